@@ -1,0 +1,13 @@
+"""dl_sound_classification_b200 -- B200-native waveform -> log-mel fbank frontend.
+
+Drop-in for the CPU torchaudio feature path of youssefg7/dl-sound-classification
+(``src/datasets/preprocessing.py``), built as hand-written sm_100a CUDA behind the C ABI
+in ``include/b200fbank.h``.  Importing the package loads ``lib/libb200fbank.so``; it
+raises if the library has not been built -- there is no CPU fallback.
+"""
+from . import _capi
+from .frontend import AST_FBANK_KWARGS, FbankFrontend, launch_count
+from .kaldi import fbank
+
+__all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi"]
+__version__ = "0.1.0"

@@ -1,0 +1,506 @@
+// libb200fbank.so -- C ABI (include/b200fbank.h) over the sm_100a fbank kernels.
+//
+// Host side: builds the immutable tables of a plan in float64 (polyphase taps, window,
+// twiddles, sparse mel weights), uploads them once, validates arguments the way
+// torchaudio asserts them, and launches kernels on the caller's stream.  No CPU compute
+// path exists: device calls on a host-only plan fail with B200FBANK_ERR_NO_DEVICE.
+#include "../../include/b200fbank.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fbank_generic.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return fail(B200FBANK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
+  } while (0)
+
+struct RateHost {
+  int hz = 0, orig = 0, nw = 0, width = 0, klen = 0, L = 0, identity = 0;
+  std::vector<float> dense;   // [nw][klen]
+  std::vector<float> sparse;  // [nw][L]
+  std::vector<int> k0;        // [nw]
+};
+
+// Hann-windowed sinc taps: torchaudio/functional/functional.py:1305-1402 as called by
+// transforms.Resample (dtype=None): float64 grid, float32 phase term, float32 result.
+void build_rate(RateHost& r, int hz, int target_hz, int lpw, double rolloff) {
+  r.hz = hz;
+  if (hz == target_hz) {
+    r.identity = 1; r.orig = r.nw = 1; r.width = 0; r.klen = 1; r.L = 1;
+    r.dense = {1.f}; r.sparse = {1.f}; r.k0 = {0};
+    return;
+  }
+  int g = std::gcd(hz, target_hz);
+  r.orig = hz / g; r.nw = target_hz / g;
+  double base_freq = std::min(r.orig, r.nw) * rolloff;
+  r.width = (int)std::ceil(lpw * r.orig / base_freq);
+  r.klen = 2 * r.width + r.orig;
+  r.dense.assign((size_t)r.nw * r.klen, 0.f);
+  const double scale = base_freq / r.orig;
+  for (int p = 0; p < r.nw; ++p) {
+    const double phase = (double)((float)(-p) / (float)r.nw);   // int64 tensor / int -> float32
+    for (int k = 0; k < r.klen; ++k) {
+      double t = (phase + (double)(k - r.width) / r.orig) * base_freq;
+      t = std::min(std::max(t, (double)-lpw), (double)lpw);
+      double c = std::cos(t * M_PI / lpw / 2);
+      double w = c * c;
+      t *= M_PI;
+      double s = (t == 0.0) ? 1.0 : std::sin(t) / t;
+      r.dense[(size_t)p * r.klen + k] = (float)(s * (w * scale));
+    }
+  }
+  // keep the run of taps that are not (numerically) zero; the clamp makes everything outside
+  // +-lpw zero crossings cos^2(pi/2) ~ 1e-33
+  std::vector<int> first(r.nw), last(r.nw);
+  r.L = 1;
+  for (int p = 0; p < r.nw; ++p) {
+    int a = r.klen, b = -1;
+    for (int k = 0; k < r.klen; ++k)
+      if (std::fabs(r.dense[(size_t)p * r.klen + k]) > 1e-25f) { a = std::min(a, k); b = std::max(b, k); }
+    if (b < 0) { a = 0; b = 0; }
+    first[p] = a; last[p] = b;
+    r.L = std::max(r.L, b - a + 1);
+  }
+  r.k0.resize(r.nw);
+  r.sparse.assign((size_t)r.nw * r.L, 0.f);
+  for (int p = 0; p < r.nw; ++p) {
+    int a = std::min(first[p], r.klen - r.L);
+    r.k0[p] = a;
+    for (int j = 0; j < r.L; ++j) {
+      float v = r.dense[(size_t)p * r.klen + a + j];
+      r.sparse[(size_t)p * r.L + j] = (a + j >= first[p] && a + j <= last[p]) ? v : 0.f;
+    }
+  }
+}
+
+double mel_scale(double f) { return 1127.0 * std::log(1.0 + f / 700.0); }
+double inv_mel_scale(double m) { return 700.0 * (std::exp(m / 1127.0) - 1.0); }
+
+// vtln_warp_freq, torchaudio/compliance/kaldi.py:334-407 (assignment order preserved)
+double vtln_warp_freq(double vl, double vh, double lo, double hi, double warp, double f) {
+  const double l = vl * std::max(1.0, warp), h = vh * std::min(1.0, warp);
+  const double scale = 1.0 / warp, Fl = scale * l, Fh = scale * h;
+  const double sl = (Fl - lo) / (l - lo), sr = (hi - Fh) / (hi - h);
+  double res = 0.0;
+  if (f >= h) res = hi + sr * (f - hi);
+  if (f < h) res = scale * f;
+  if (f < l) res = lo + sl * (f - lo);
+  if (f < lo || f > hi) res = f;
+  return res;
+}
+
+}  // namespace
+
+struct b200fbank_plan {
+  b200fbank_opts o;
+  int device = -1;
+  int shift = 0, size = 0, padded = 0, log2n = 0, n_mel = 0, n_cols = 0;
+  std::vector<RateHost> rates;
+  std::vector<float> window;          // [size]
+  std::vector<float> mel_dense;       // [n_mel][padded/2]
+  std::vector<int> mel_start, mel_cnt, mel_off;
+  std::vector<float> mel_w;
+  std::vector<float> twiddle;         // [padded/2][2]
+  // device copies
+  void* d_blob = nullptr;
+  b200::FbankParams base;             // table pointers + scalars filled once
+  int generic_threads = 256;
+  size_t generic_smem = 0;
+};
+
+namespace {
+
+int build_tables(b200fbank_plan* p) {
+  const b200fbank_opts& o = p->o;
+  // _get_waveform_and_window_properties, kaldi.py:125-151 (same float64 expression order)
+  p->shift = (int)(o.sample_frequency * o.frame_shift * 0.001);
+  p->size = (int)(o.sample_frequency * o.frame_length * 0.001);
+  if (o.sample_frequency <= 0) return fail(B200FBANK_ERR_INVALID, "`sample_frequency` must be greater than zero");
+  if (p->size < 2) return fail(B200FBANK_ERR_INVALID, "choose a window size %d that is [2, len(waveform)]", p->size);
+  if (p->shift <= 0) return fail(B200FBANK_ERR_INVALID, "`window_shift` must be greater than 0");
+  int pow2 = 1;
+  while (pow2 < p->size) pow2 <<= 1;
+  p->padded = o.round_to_power_of_two ? pow2 : p->size;
+  if (p->padded % 2 != 0)
+    return fail(B200FBANK_ERR_INVALID, "the padded `window_size` must be divisible by two. use `round_to_power_of_two` or change `frame_length`");
+  if (p->padded != pow2)
+    return fail(B200FBANK_ERR_UNSUPPORTED, "round_to_power_of_two=False with window size %d: only power-of-two FFT sizes are implemented", p->size);
+  if (p->padded > 4096) return fail(B200FBANK_ERR_UNSUPPORTED, "FFT size %d > 4096", p->padded);
+  p->log2n = 0;
+  while ((1 << p->log2n) < p->padded) ++p->log2n;
+  if (!(o.preemphasis_coefficient >= 0.0 && o.preemphasis_coefficient <= 1.0))
+    return fail(B200FBANK_ERR_INVALID, "`preemphasis_coefficient` must be between [0,1]");
+  if (o.energy_floor < 0.0) return fail(B200FBANK_ERR_INVALID, "energy_floor must be >= 0");
+  if (o.frontend != B200FBANK_FRONTEND_KALDI_FBANK)
+    return fail(B200FBANK_ERR_UNSUPPORTED, "frontend %d not implemented", o.frontend);
+
+  // window, kaldi.py:86-113
+  p->window.resize(p->size);
+  const double a = 2.0 * M_PI / (p->size - 1);
+  for (int i = 0; i < p->size; ++i) {
+    double w;
+    switch (o.window_type) {
+      case B200FBANK_WINDOW_HANNING: w = 0.5 - 0.5 * std::cos(a * i); break;
+      case B200FBANK_WINDOW_HAMMING: w = 0.54 - 0.46 * std::cos(a * i); break;
+      case B200FBANK_WINDOW_POVEY:   w = std::pow((double)(float)(0.5 - 0.5 * std::cos(a * i)), 0.85); break;
+      case B200FBANK_WINDOW_RECTANGULAR: w = 1.0; break;
+      case B200FBANK_WINDOW_BLACKMAN:
+        w = o.blackman_coeff - 0.5 * std::cos(a * i) + (0.5 - o.blackman_coeff) * std::cos(2 * a * i); break;
+      default: return fail(B200FBANK_ERR_INVALID, "Invalid window type %d", o.window_type);
+    }
+    p->window[i] = (float)w;
+  }
+
+  // twiddles
+  const int N = p->padded, NB = N / 2;
+  p->twiddle.resize((size_t)NB * 2);
+  for (int k = 0; k < NB; ++k) {
+    p->twiddle[2 * k] = (float)std::cos(2.0 * M_PI * k / N);
+    p->twiddle[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / N));
+  }
+
+  // get_mel_banks, kaldi.py:436-511, evaluated in float64
+  p->n_mel = o.num_mel_bins;
+  if (p->n_mel <= 3) return fail(B200FBANK_ERR_INVALID, "Must have at least 3 mel bins");
+  p->n_cols = p->n_mel + (o.use_energy ? 1 : 0);
+  const double nyquist = 0.5 * o.sample_frequency;
+  double high = o.high_freq, low = o.low_freq;
+  if (high <= 0.0) high += nyquist;
+  if (!((0.0 <= low && low < nyquist) && (0.0 < high && high <= nyquist) && (low < high)))
+    return fail(B200FBANK_ERR_INVALID, "Bad values in options: low-freq %g and high-freq %g vs. nyquist %g", low, high, nyquist);
+  const double bin_width = o.sample_frequency / N;
+  const double mel_low = mel_scale(low), mel_high = mel_scale(high);
+  const double delta = (mel_high - mel_low) / (p->n_mel + 1);
+  double vh = o.vtln_high;
+  if (vh < 0.0) vh += nyquist;
+  const bool warp = o.vtln_warp != 1.0;
+  if (warp && !((low < o.vtln_low && o.vtln_low < high) && (0.0 < vh && vh < high) && (o.vtln_low < vh)))
+    return fail(B200FBANK_ERR_INVALID, "Bad values in options: vtln-low %g and vtln-high %g, versus low-freq %g and high-freq %g", o.vtln_low, vh, low, high);
+  p->mel_dense.assign((size_t)p->n_mel * NB, 0.f);
+  p->mel_start.resize(p->n_mel); p->mel_cnt.resize(p->n_mel); p->mel_off.resize(p->n_mel);
+  p->mel_w.clear();
+  for (int m = 0; m < p->n_mel; ++m) {
+    double left = mel_low + m * delta, center = mel_low + (m + 1.0) * delta, right = mel_low + (m + 2.0) * delta;
+    if (warp) {
+      left = mel_scale(vtln_warp_freq(o.vtln_low, vh, low, high, o.vtln_warp, inv_mel_scale(left)));
+      center = mel_scale(vtln_warp_freq(o.vtln_low, vh, low, high, o.vtln_warp, inv_mel_scale(center)));
+      right = mel_scale(vtln_warp_freq(o.vtln_low, vh, low, high, o.vtln_warp, inv_mel_scale(right)));
+    }
+    int first = NB, last = -1;
+    for (int k = 0; k < NB; ++k) {
+      const double mel = mel_scale(bin_width * k);
+      const double up = (mel - left) / (center - left), down = (right - mel) / (right - center);
+      double w;
+      if (!warp) w = std::max(0.0, std::min(up, down));
+      else w = (mel > left && mel <= center) ? up : ((mel > center && mel < right) ? down : 0.0);
+      const float wf = (float)w;
+      p->mel_dense[(size_t)m * NB + k] = wf;
+      if (wf != 0.f) { first = std::min(first, k); last = std::max(last, k); }
+    }
+    p->mel_off[m] = (int)p->mel_w.size();
+    if (last < 0) { p->mel_start[m] = 0; p->mel_cnt[m] = 0; continue; }
+    p->mel_start[m] = first; p->mel_cnt[m] = last - first + 1;
+    for (int k = first; k <= last; ++k) p->mel_w.push_back(p->mel_dense[(size_t)m * NB + k]);
+  }
+
+  // rate table
+  if (o.n_rates < 1 || o.n_rates > B200FBANK_MAX_RATES)
+    return fail(B200FBANK_ERR_INVALID, "n_rates must be in [1, %d]", B200FBANK_MAX_RATES);
+  if (o.lowpass_filter_width <= 0) return fail(B200FBANK_ERR_INVALID, "Low pass filter width should be positive.");
+  const int target = (int)o.sample_frequency;
+  p->rates.resize(o.n_rates);
+  for (int i = 0; i < o.n_rates; ++i) {
+    if (o.orig_rates[i] <= 0) return fail(B200FBANK_ERR_INVALID, "orig_rates[%d] must be positive", i);
+    if (o.orig_rates[i] != target && (double)target != o.sample_frequency)
+      return fail(B200FBANK_ERR_INVALID, "Frequencies must be of integer type to ensure quality resampling computation.");
+    build_rate(p->rates[i], o.orig_rates[i], target, o.lowpass_filter_width, o.rolloff);
+  }
+  return 0;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Shared-memory carve-up of the generic kernel for a tile of F frames.
+void generic_smem_layout(const b200fbank_plan* p, int F, int* sy, int* sx, int* sz) {
+  const int ny = (F - 1) * p->shift + p->size;
+  int nx = 0;
+  for (const RateHost& r : p->rates) {
+    if (r.identity) continue;
+    int q = ny / r.nw + 2;
+    nx = std::max(nx, q * r.orig + r.klen);
+  }
+  nx = std::max(nx, F * (p->padded / 2));
+  *sy = (int)align_up(ny, 4);
+  *sx = (int)align_up(nx, 4);
+  *sz = F * p->padded;
+}
+
+int upload(b200fbank_plan* p) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  // one blob: [window][twiddle][mel_w][mel_start][mel_cnt][mel_off]{[taps][k0]}*
+  std::vector<char> blob;
+  auto put = [&](const void* src, size_t bytes) {
+    size_t off = align_up(blob.size(), 16);
+    blob.resize(off + bytes);
+    if (bytes) memcpy(blob.data() + off, src, bytes);
+    return off;
+  };
+  size_t o_win = put(p->window.data(), p->window.size() * 4);
+  size_t o_tw = put(p->twiddle.data(), p->twiddle.size() * 4);
+  size_t o_mw = put(p->mel_w.data(), p->mel_w.size() * 4);
+  size_t o_ms = put(p->mel_start.data(), p->mel_start.size() * 4);
+  size_t o_mc = put(p->mel_cnt.data(), p->mel_cnt.size() * 4);
+  size_t o_mo = put(p->mel_off.data(), p->mel_off.size() * 4);
+  std::vector<size_t> o_taps, o_k0;
+  for (const RateHost& r : p->rates) {
+    o_taps.push_back(put(r.sparse.data(), r.sparse.size() * 4));
+    o_k0.push_back(put(r.k0.data(), r.k0.size() * 4));
+  }
+  CUDA_TRY(cudaMalloc(&p->d_blob, blob.size()));
+  CUDA_TRY(cudaMemcpy(p->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  char* d = (char*)p->d_blob;
+  b200::FbankParams& k = p->base;
+  memset(&k, 0, sizeof k);
+  const b200fbank_opts& o = p->o;
+  for (size_t i = 0; i < p->rates.size(); ++i) {
+    const RateHost& r = p->rates[i];
+    k.rates[i] = b200::RateDev{r.orig, r.nw, r.width, r.klen, r.L, r.identity,
+                               (const float*)(d + o_taps[i]), (const int*)(d + o_k0[i])};
+  }
+  k.shift = p->shift; k.size = p->size; k.padded = p->padded; k.log2n = p->log2n;
+  k.snip_edges = o.snip_edges; k.remove_dc = o.remove_dc_offset; k.raw_energy = o.raw_energy;
+  k.use_energy = o.use_energy; k.htk_compat = o.htk_compat; k.use_power = o.use_power; k.use_log = o.use_log_fbank;
+  k.preemph = (float)o.preemphasis_coefficient;
+  k.has_energy_floor = o.energy_floor != 0.0;
+  k.log_energy_floor = k.has_energy_floor ? (float)std::log(o.energy_floor) : 0.f;
+  k.window = (const float*)(d + o_win);
+  k.twiddle = (const float2*)(d + o_tw);
+  k.n_mel = p->n_mel; k.n_cols = p->n_cols;
+  k.mel_start = (const int*)(d + o_ms); k.mel_cnt = (const int*)(d + o_mc); k.mel_off = (const int*)(d + o_mo);
+  k.mel_w = (const float*)(d + o_mw);
+
+  // pick the largest tile that fits comfortably (two CTAs per SM when possible)
+  int F = 16;
+  for (; F >= 2; F >>= 1) {
+    int sy, sx, sz;
+    generic_smem_layout(p, F, &sy, &sx, &sz);
+    size_t bytes = (size_t)(sy + sx + sz + F) * 4;
+    if (bytes <= 110 * 1024 || (F == 2 && bytes <= 227 * 1024)) {
+      k.tile_frames = F; k.smem_y = sy; k.smem_x = sx; k.smem_z = sz;
+      p->generic_smem = bytes;
+      break;
+    }
+  }
+  if (F < 2) return fail(B200FBANK_ERR_UNSUPPORTED, "configuration does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->generic_smem));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->generic_smem));
+  return 0;
+}
+
+int check_device_call(const b200fbank_plan* p, const void* wav, const int64_t* offsets, int64_t clip_samples, int B) {
+  if (!p) return fail(B200FBANK_ERR_INVALID, "plan is NULL");
+  if (p->device < 0) return fail(B200FBANK_ERR_NO_DEVICE, "host-only plan (device=-1): no CPU compute path exists");
+  if (B < 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0");
+  if (B > 0 && !wav) return fail(B200FBANK_ERR_INVALID, "d_wav is NULL");
+  if (!offsets && clip_samples <= 0 && B > 0) return fail(B200FBANK_ERR_INVALID, "clip_samples must be > 0 when d_offsets is NULL");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200fbank_abi_version(void) { return B200FBANK_ABI_VERSION; }
+
+void b200fbank_default_opts(b200fbank_opts* o) {
+  memset(o, 0, sizeof *o);
+  o->blackman_coeff = 0.42; o->energy_floor = 1.0; o->frame_length = 25.0; o->frame_shift = 10.0;
+  o->high_freq = 0.0; o->low_freq = 20.0; o->preemphasis_coefficient = 0.97; o->sample_frequency = 16000.0;
+  o->vtln_high = -500.0; o->vtln_low = 100.0; o->vtln_warp = 1.0;
+  o->num_mel_bins = 23; o->window_type = B200FBANK_WINDOW_POVEY;
+  o->htk_compat = 0; o->raw_energy = 1; o->remove_dc_offset = 1; o->round_to_power_of_two = 1;
+  o->snip_edges = 1; o->subtract_mean = 0; o->use_energy = 0; o->use_log_fbank = 1; o->use_power = 1;
+  o->n_rates = 1; o->orig_rates[0] = 16000; o->lowpass_filter_width = 6; o->rolloff = 0.99;
+  o->frontend = B200FBANK_FRONTEND_KALDI_FBANK; o->n_fft = 1024; o->hop_length = 160; o->win_length = 400;
+  o->top_db = 80.0;
+}
+
+int b200fbank_plan_create(const b200fbank_opts* o, int device, b200fbank_plan** out) {
+  if (!o || !out) return fail(B200FBANK_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  b200fbank_plan* p = new b200fbank_plan();
+  p->o = *o;
+  p->device = device;
+  int rc = build_tables(p);
+  if (rc == 0 && device >= 0) rc = upload(p);
+  if (rc != 0) { b200fbank_plan_destroy(p); return rc; }
+  *out = p;
+  return 0;
+}
+
+void b200fbank_plan_destroy(b200fbank_plan* p) {
+  if (!p) return;
+  if (p->d_blob) cudaFree(p->d_blob);
+  delete p;
+}
+
+const char* b200fbank_last_error(void) { return g_err.c_str(); }
+
+int64_t b200fbank_resampled_length(const b200fbank_plan* p, int64_t n, int rate_id) {
+  if (!p || rate_id < 0 || rate_id >= (int)p->rates.size()) return fail(B200FBANK_ERR_INVALID, "bad rate_id %d", rate_id);
+  const RateHost& r = p->rates[rate_id];
+  return r.identity ? n : b200::resampled_length(n, r.orig, r.nw);
+}
+
+int64_t b200fbank_num_frames(const b200fbank_plan* p, int64_t n, int rate_id) {
+  int64_t n_rs = b200fbank_resampled_length(p, n, rate_id);
+  if (n_rs < 0) return n_rs;
+  return b200::num_frames(n_rs, p->size, p->shift, p->o.snip_edges);
+}
+
+int b200fbank_num_cols(const b200fbank_plan* p) { return p ? p->n_cols : fail(B200FBANK_ERR_INVALID, "plan is NULL"); }
+
+int64_t b200fbank_plan_table(const b200fbank_plan* p, int table, int arg, float* dst, int64_t cap) {
+  if (!p) return fail(B200FBANK_ERR_INVALID, "plan is NULL");
+  const std::vector<float>* v = nullptr;
+  switch (table) {
+    case B200FBANK_TABLE_WINDOW: v = &p->window; break;
+    case B200FBANK_TABLE_MEL_DENSE: v = &p->mel_dense; break;
+    case B200FBANK_TABLE_TAPS_DENSE:
+      if (arg < 0 || arg >= (int)p->rates.size()) return fail(B200FBANK_ERR_INVALID, "bad rate_id %d", arg);
+      v = &p->rates[arg].dense; break;
+    default: return fail(B200FBANK_ERR_INVALID, "bad table %d", table);
+  }
+  int64_t n = (int64_t)v->size();
+  if (dst) memcpy(dst, v->data(), (size_t)std::min(n, cap) * 4);
+  return n;
+}
+
+int b200fbank_plan_info(const b200fbank_plan* p, int arg, int64_t info[8]) {
+  if (!p || !info) return fail(B200FBANK_ERR_INVALID, "NULL argument");
+  if (arg < 0 || arg >= (int)p->rates.size()) return fail(B200FBANK_ERR_INVALID, "bad rate_id %d", arg);
+  const RateHost& r = p->rates[arg];
+  info[0] = p->shift; info[1] = p->size; info[2] = p->padded; info[3] = (int64_t)p->rates.size();
+  info[4] = r.orig; info[5] = r.nw; info[6] = r.width; info[7] = r.L;
+  return 0;
+}
+
+int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                      int64_t clip_samples, const int32_t* d_rate_id, int B,
+                      const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                      float target_mean, float target_std, int out_frames, int layout,
+                      float* d_out, int32_t* d_n_frames, void* stream) {
+  int rc = check_device_call(p, d_wav, d_offsets, clip_samples, B);
+  if (rc) return rc;
+  if (out_frames <= 0) return fail(B200FBANK_ERR_INVALID, "out_frames must be > 0");
+  if (layout != B200FBANK_LAYOUT_BTF && layout != B200FBANK_LAYOUT_BFT) return fail(B200FBANK_ERR_INVALID, "bad layout %d", layout);
+  if (n_stats != 0 && n_stats != 1 && n_stats != p->n_cols)
+    return fail(B200FBANK_ERR_INVALID, "n_stats must be 0, 1 or n_cols=%d (got %d)", p->n_cols, n_stats);
+  if (n_stats != 0 && (!d_mean || !d_std)) return fail(B200FBANK_ERR_INVALID, "d_mean/d_std are NULL");
+  if (!d_out) return fail(B200FBANK_ERR_INVALID, "d_out is NULL");
+  if (B == 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  b200::FbankParams k = p->base;
+  k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
+  k.out_frames = out_frames; k.layout = layout; k.out = d_out; k.n_frames_out = d_n_frames;
+  k.masks = d_masks; k.mean = d_mean; k.std = d_std; k.n_stats = n_stats;
+  k.target_mean = target_mean; k.target_std = target_std;
+  const bool cms = p->o.subtract_mean != 0;
+  if (cms) { k.masks = nullptr; k.n_stats = 0; }     // raw features first, cms_kernel finishes
+  k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
+  const int64_t grid = (int64_t)B * k.tiles;
+  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles = %lld exceeds the grid limit", (long long)grid);
+  b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (cms) {
+    k.masks = d_masks; k.n_stats = n_stats;
+    b200::cms_kernel<<<B, 128, 0, st>>>(k);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                               int64_t clip_samples, const int32_t* d_rate_id, int B, int max_frames,
+                               double* d_sums, void* stream) {
+  int rc = check_device_call(p, d_wav, d_offsets, clip_samples, B);
+  if (rc) return rc;
+  if (max_frames <= 0) return fail(B200FBANK_ERR_INVALID, "max_frames must be > 0");
+  if (!d_sums) return fail(B200FBANK_ERR_INVALID, "d_sums is NULL");
+  if (p->o.subtract_mean) return fail(B200FBANK_ERR_UNSUPPORTED, "stats with subtract_mean=True are identically zero-mean; not implemented");
+  if (B == 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  b200::FbankParams k = p->base;
+  k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
+  k.max_frames = max_frames; k.sums = d_sums;
+  k.tiles = (max_frames + k.tile_frames - 1) / k.tile_frames;
+  const int64_t grid = (int64_t)B * k.tiles;
+  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+  b200::fbank_generic_kernel<true><<<(unsigned)grid, p->generic_threads, p->generic_smem, (cudaStream_t)stream>>>(k);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200fbank_resample(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                       int64_t clip_samples, const int32_t* d_rate_id, int B, float* d_out,
+                       const int64_t* d_out_offsets, int64_t out_clip_samples, void* stream) {
+  int rc = check_device_call(p, d_wav, d_offsets, clip_samples, B);
+  if (rc) return rc;
+  if (!d_out) return fail(B200FBANK_ERR_INVALID, "d_out is NULL");
+  if (out_clip_samples <= 0) return fail(B200FBANK_ERR_INVALID, "out_clip_samples (longest resampled clip) must be > 0");
+  if (B == 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int chunk = 4096;
+  int nx = 0;
+  for (const RateHost& r : p->rates)
+    if (!r.identity) nx = std::max(nx, (chunk / r.nw + 2) * r.orig + r.klen);
+  const size_t smem = (size_t)(chunk + align_up(std::max(nx, 4), 4)) * 4;
+  if (smem > 227 * 1024) return fail(B200FBANK_ERR_UNSUPPORTED, "resample ratio needs %zu B of shared memory", smem);
+  CUDA_TRY(cudaFuncSetAttribute(b200::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  b200::FbankParams k = p->base;
+  k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
+  k.tiles = (int)((out_clip_samples + chunk - 1) / chunk);
+  const int64_t grid = (int64_t)B * k.tiles;
+  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+  b200::resample_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(k, d_out, d_out_offsets, out_clip_samples, chunk);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int64_t b200fbank_launch_count(int reset) {
+  int64_t n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+}  // extern "C"

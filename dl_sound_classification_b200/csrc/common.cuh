@@ -1,0 +1,78 @@
+// Shared device-side parameter blocks and index arithmetic for the fbank kernels.
+//
+// Index arithmetic that the reference leaves to torch views is restated here once, as
+// __host__ __device__ functions, so the CPU test-suite can pin it through the C ABI
+// (b200fbank_num_frames / b200fbank_resampled_length) without a GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200_MAX_RATES 8
+#define B200_FLT_EPSILON 1.1920928955078125e-07f   // torchaudio/compliance/kaldi.py:26
+
+namespace b200 {
+
+// One entry of the polyphase table (torchaudio/functional/functional.py:1305-1402).
+struct RateDev {
+  int orig;          // gcd-reduced input rate  (441 for 44.1 kHz -> 16 kHz)
+  int nw;            // gcd-reduced output rate (160)
+  int width;         // left zero padding of the torchaudio conv (17)
+  int klen;          // 2*width + orig: dense taps per phase (475)
+  int L;             // taps kept per phase after dropping exact zeros (34)
+  int identity;      // 1: this rate needs no resampling
+  const float* taps; // [nw][L]
+  const int* k0;     // [nw] dense index of the first kept tap of each phase
+};
+
+struct FbankParams {
+  // input
+  const float* wav;
+  const int64_t* offsets;    // [B+1] or nullptr
+  int64_t clip_samples;      // dense row length when offsets == nullptr
+  const int32_t* rate_id;    // [B] or nullptr
+  int B;
+  RateDev rates[B200_MAX_RATES];
+  // framing (torchaudio/compliance/kaldi.py:125-151)
+  int shift, size, padded, log2n;
+  int snip_edges, remove_dc, raw_energy, use_energy, htk_compat, use_power, use_log;
+  float preemph, log_energy_floor; int has_energy_floor;
+  const float* window;       // [size]
+  const float2* twiddle;     // [padded/2]  W_N^k = (cos 2 pi k/N, -sin 2 pi k/N)
+  // sparse mel (get_mel_banks, kaldi.py:436-511): bin m = sum_j w[off[m]+j] * P[start[m]+j]
+  int n_mel, n_cols;
+  const int* mel_start; const int* mel_cnt; const int* mel_off; const float* mel_w;
+  // epilogue
+  int out_frames, layout;
+  const int32_t* masks;      // [B][4] or nullptr
+  const float* mean; const float* std; int n_stats;
+  float target_mean, target_std;
+  float* out;
+  int32_t* n_frames_out;
+  double* sums;              // stats mode: [2*n_cols+1]
+  int max_frames;            // stats mode frame cap
+  int tile_frames;           // F: frames per CTA
+  int tiles;                 // CTAs per clip (grid = B * tiles, clip-major)
+  // dynamic shared memory carve-up (in floats)
+  int smem_y, smem_x, smem_z;
+};
+
+__host__ __device__ inline int64_t resampled_length(int64_t n, int orig, int nw) {
+  // ceil(new * length / orig), functional.py:1427
+  return (n * (int64_t)nw + orig - 1) / orig;
+}
+
+__host__ __device__ inline int64_t num_frames(int64_t n, int size, int shift, int snip_edges) {
+  // _get_strided, kaldi.py:63-69
+  if (snip_edges) return n < size ? 0 : 1 + (n - size) / shift;
+  return (n + shift / 2) / shift;
+}
+
+// Virtual sample index -> real index for snip_edges=False (kaldi.py:70-80): the signal is
+// mirrored about -1/2 on the left and about n-1/2 on the right.
+__host__ __device__ inline int64_t reflect_index(int64_t v, int64_t n) {
+  if (v < 0) return -1 - v;
+  if (v >= n) return 2 * n - 1 - v;
+  return v;
+}
+
+}  // namespace b200

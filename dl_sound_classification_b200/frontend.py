@@ -1,0 +1,219 @@
+"""Batched B200 frontend: a plan (immutable tables on one GPU) + fused execute.
+
+This is the host side of the C ABI in ``include/b200fbank.h``.  torch is used for
+device memory, streams and the custom-op registration only; every stage of the
+path runs in ``libb200fbank.so``.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _capi as K
+
+_KALDI_DEFAULTS = dict(
+    blackman_coeff=0.42, energy_floor=1.0, frame_length=25.0, frame_shift=10.0, high_freq=0.0,
+    htk_compat=False, low_freq=20.0, num_mel_bins=23, preemphasis_coefficient=0.97, raw_energy=True,
+    remove_dc_offset=True, round_to_power_of_two=True, sample_frequency=16000.0, snip_edges=True,
+    subtract_mean=False, use_energy=False, use_log_fbank=True, use_power=True, vtln_high=-500.0,
+    vtln_low=100.0, vtln_warp=1.0, window_type="povey",
+)
+
+AST_FBANK_KWARGS = dict(htk_compat=True, sample_frequency=16000.0, use_energy=False, window_type="hanning",
+                        num_mel_bins=128, frame_shift=10.0)
+
+_plans: Dict[int, "FbankFrontend"] = {}
+_plans_lock = threading.Lock()
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("dl_sound_classification_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    d = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError(f"device must be a CUDA device, got {d}")
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
+def make_opts(orig_rates: Sequence[int], lowpass_filter_width: int = 6, rolloff: float = 0.99, **kaldi) -> K.Opts:
+    unknown = set(kaldi) - set(_KALDI_DEFAULTS)
+    if unknown:
+        raise TypeError(f"unknown kaldi.fbank option(s): {sorted(unknown)}")
+    kw = dict(_KALDI_DEFAULTS)
+    kw.update(kaldi)
+    if kw["window_type"] not in K.WINDOW_TYPES:
+        raise Exception("Invalid window type " + str(kw["window_type"]))      # torchaudio kaldi.py:113
+    o = K.default_opts()
+    for name in ("blackman_coeff", "energy_floor", "frame_length", "frame_shift", "high_freq", "low_freq",
+                 "preemphasis_coefficient", "sample_frequency", "vtln_high", "vtln_low", "vtln_warp"):
+        setattr(o, name, float(kw[name]))
+    o.num_mel_bins = int(kw["num_mel_bins"])
+    o.window_type = K.WINDOW_TYPES[kw["window_type"]]
+    for name in ("htk_compat", "raw_energy", "remove_dc_offset", "round_to_power_of_two", "snip_edges",
+                 "subtract_mean", "use_energy", "use_log_fbank", "use_power"):
+        setattr(o, name, int(bool(kw[name])))
+    rates = [int(r) for r in orig_rates]
+    if not 1 <= len(rates) <= K.MAX_RATES:
+        raise ValueError(f"between 1 and {K.MAX_RATES} input rates are supported")
+    o.n_rates = len(rates)
+    for i, r in enumerate(rates):
+        o.orig_rates[i] = r
+    o.lowpass_filter_width = int(lowpass_filter_width)
+    o.rolloff = float(rolloff)
+    return o
+
+
+class FbankFrontend:
+    """waveform batch -> (B, T, n_cols) or (B, 1, n_cols, T) log-mel features on one GPU.
+
+    ``orig_rates`` is the table of input sample rates a clip may have
+    (``rate_ids`` index it); the fbank itself runs at ``sample_frequency``.
+    """
+
+    def __init__(self, orig_rates: Sequence[int] = (16000,), device=None, lowpass_filter_width: int = 6,
+                 rolloff: float = 0.99, host_only: bool = False, **kaldi):
+        self.orig_rates = tuple(int(r) for r in orig_rates)
+        self.kaldi = dict(_KALDI_DEFAULTS, **kaldi)
+        opts = make_opts(self.orig_rates, lowpass_filter_width, rolloff, **kaldi)
+        if host_only:
+            self.device = None
+            self.plan = K.Plan(opts, -1)
+        else:
+            self.device = _require_cuda(device)
+            self.plan = K.Plan(opts, self.device.index)
+        self.n_cols = self.plan.n_cols
+        with _plans_lock:
+            self.plan_id = (max(_plans) + 1) if _plans else 1
+            _plans[self.plan_id] = self
+
+    # -- host arithmetic ---------------------------------------------------------------
+    def num_frames(self, n_samples: int, rate_id: int = 0) -> int:
+        return self.plan.num_frames(int(n_samples), int(rate_id))
+
+    def resampled_length(self, n_samples: int, rate_id: int = 0) -> int:
+        return self.plan.resampled_length(int(n_samples), int(rate_id))
+
+    def rate_id(self, sample_rate: int) -> int:
+        try:
+            return self.orig_rates.index(int(sample_rate))
+        except ValueError:
+            raise ValueError(f"sample rate {sample_rate} is not in this plan's rate table {self.orig_rates}") from None
+
+    # -- argument plumbing -------------------------------------------------------------
+    def _dev(self, t: Optional[torch.Tensor], dtype, what: str) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != dtype:
+            t = t.to(device=self.device, dtype=dtype, non_blocking=True)
+        return t.contiguous()
+
+    def _wave_args(self, wav, offsets, rate_ids):
+        if self.device is None:
+            raise K.B200FbankError(K.ERR_NO_DEVICE, "host-only plan: no CPU compute path exists")
+        if not wav.is_floating_point():
+            raise TypeError(f"Expected floating point type for waveform tensor, but received {wav.dtype}.")
+        wav = self._dev(wav, torch.float32, "wav")
+        if offsets is None:
+            if wav.dim() != 2:
+                raise ValueError("dense batches must be (B, n_samples); pass offsets for ragged 1-D input")
+            B, clip = int(wav.shape[0]), int(wav.shape[1])
+            off = None
+        else:
+            if wav.dim() != 1:
+                raise ValueError("ragged input must be a flat 1-D tensor with offsets[B+1]")
+            off = self._dev(offsets, torch.int64, "offsets")
+            B, clip = int(off.numel()) - 1, 0
+        rid = self._dev(rate_ids, torch.int32, "rate_ids")
+        if rid is not None and rid.numel() != B:
+            raise ValueError("rate_ids must have one entry per clip")
+        return wav, off, clip, rid, B
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    # -- device calls ------------------------------------------------------------------
+    def __call__(self, wav: torch.Tensor, out_frames: int, offsets: Optional[torch.Tensor] = None,
+                 rate_ids: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None,
+                 mean: Union[None, float, torch.Tensor] = None, std: Union[None, float, torch.Tensor] = None,
+                 target_mean: float = 0.0, target_std: float = 0.5, layout: str = "btf",
+                 out: Optional[torch.Tensor] = None, return_n_frames: bool = True
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """The fused path (``b200fbank_execute``).  ``mean``/``std``: None (no
+        normalisation), scalar, or per-column ``[n_cols]``; output
+        ``(x-mean)/std*target_std+target_mean``.  ``masks``: int32 ``(B, 4)`` =
+        ``t_start, t_len, f_start, f_len``; cells zeroed after normalisation."""
+        wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
+        lay = {"btf": K.LAYOUT_BTF, "bft": K.LAYOUT_BFT}[layout]
+        shape = (B, int(out_frames), self.n_cols) if lay == K.LAYOUT_BTF else (B, 1, self.n_cols, int(out_frames))
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 {shape} tensor on {self.device}")
+        nfr = torch.empty(B, dtype=torch.int32, device=self.device) if return_n_frames else None
+        mk = self._dev(masks, torch.int32, "masks")
+        if mk is not None and tuple(mk.shape) != (B, 4):
+            raise ValueError("masks must be (B, 4) int32: t_start, t_len, f_start, f_len")
+        if (mean is None) != (std is None):
+            raise ValueError("pass both mean and std or neither")
+        mt = st = None
+        n_stats = 0
+        if mean is not None:
+            mt = self._dev(torch.as_tensor(mean, dtype=torch.float32).reshape(-1), torch.float32, "mean")
+            st = self._dev(torch.as_tensor(std, dtype=torch.float32).reshape(-1), torch.float32, "std")
+            if mt.numel() != st.numel():
+                raise ValueError("mean and std must have the same number of elements")
+            n_stats = int(mt.numel())
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            K.check(K.lib.b200fbank_execute(
+                self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B, self._ptr(mk),
+                self._ptr(mt), self._ptr(st), n_stats, float(target_mean), float(target_std), int(out_frames), lay,
+                out.data_ptr(), self._ptr(nfr), stream))
+        return out, nfr
+
+    def resample(self, wav: torch.Tensor, offsets: Optional[torch.Tensor] = None,
+                 rate_ids: Optional[torch.Tensor] = None, out_clip_samples: Optional[int] = None) -> torch.Tensor:
+        """``b200fbank_resample``: dense ``(B, n)`` -> ``(B, ceil(new*n/orig))``.  With
+        ``rate_ids``/ragged input the rows are ``out_clip_samples`` long (zero beyond
+        each clip's own resampled length)."""
+        wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
+        if out_clip_samples is None:
+            if off is not None or rid is not None:
+                raise ValueError("out_clip_samples is required for ragged / mixed-rate input")
+            out_clip_samples = self.resampled_length(clip, 0)
+        out = torch.zeros((B, int(out_clip_samples)), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            K.check(K.lib.b200fbank_resample(self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B,
+                                             out.data_ptr(), None, int(out_clip_samples), stream))
+        return out
+
+    def accumulate_stats(self, wav: torch.Tensor, sums: torch.Tensor, max_frames: int,
+                         offsets: Optional[torch.Tensor] = None, rate_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``b200fbank_stats_accumulate``: add this batch's per-column sum / sum of
+        squares / frame count to ``sums`` (float64 ``[2*n_cols+1]`` on the GPU)."""
+        wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
+        if sums.dtype != torch.float64 or sums.device != self.device or sums.numel() != 2 * self.n_cols + 1 \
+                or not sums.is_contiguous():
+            raise ValueError(f"sums must be a contiguous float64 [{2 * self.n_cols + 1}] tensor on {self.device}")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            K.check(K.lib.b200fbank_stats_accumulate(self.plan.handle, wav.data_ptr(), self._ptr(off), clip,
+                                                     self._ptr(rid), B, int(max_frames), sums.data_ptr(), stream))
+        return sums
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernel launches issued by this thread through the C ABI (bench.py ``gpu_launches``)."""
+    return int(K.lib.b200fbank_launch_count(1 if reset else 0))
+
+
+def get_plan(plan_id: int) -> FbankFrontend:
+    return _plans[plan_id]

@@ -1,0 +1,191 @@
+/*
+ * b200fbank.h -- C ABI of the B200-native waveform -> log-mel fbank frontend.
+ *
+ * Drop-in boundary.  The reference has NO FFI for this path: its
+ * boundary is a pair of Python call signatures, so every entry point below names the
+ * Python interface it replaces.  Paths are relative to the reference repo unless they
+ * start with "torchaudio/" (site-packages/torchaudio, the third-party library that
+ * holds the arithmetic).
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every `d_*` pointer is
+ * DEVICE memory on the plan's device; everything else is host memory.  `stream` is a
+ * cudaStream_t passed as void*.  Functions return 0 on success or a negative
+ * b200fbank_status; the message is available from b200fbank_last_error() (thread local).
+ * A plan is immutable after creation: execute() is thread-safe per (plan, stream).
+ * The library never allocates user-visible memory and never falls back to the CPU.
+ */
+#ifndef B200FBANK_H_
+#define B200FBANK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FBANK_ABI_VERSION 1
+#define B200FBANK_MAX_RATES 8
+
+typedef enum {
+  B200FBANK_OK = 0,
+  B200FBANK_ERR_INVALID = -1,      /* bad option / argument (torchaudio would assert or raise)   */
+  B200FBANK_ERR_UNSUPPORTED = -2,  /* valid in torchaudio but not implemented here (e.g. dither) */
+  B200FBANK_ERR_CUDA = -3,         /* CUDA runtime error                                          */
+  B200FBANK_ERR_NO_DEVICE = -4     /* host-only plan used for a device call                       */
+} b200fbank_status;
+
+typedef enum {                      /* torchaudio/compliance/kaldi.py:86-113 */
+  B200FBANK_WINDOW_POVEY = 0,
+  B200FBANK_WINDOW_HANNING = 1,
+  B200FBANK_WINDOW_HAMMING = 2,
+  B200FBANK_WINDOW_RECTANGULAR = 3,
+  B200FBANK_WINDOW_BLACKMAN = 4
+} b200fbank_window;
+
+typedef enum {
+  B200FBANK_LAYOUT_BTF = 0,         /* (B, T, n_cols): kaldi-native rows = frames                */
+  B200FBANK_LAYOUT_BFT = 1          /* (B, 1, n_cols, T): what src/models/ast.py:50-56 consumes  */
+} b200fbank_layout;
+
+typedef enum {
+  B200FBANK_FRONTEND_KALDI_FBANK = 0,  /* torchaudio/compliance/kaldi.py:514-645 (north_star)    */
+  B200FBANK_FRONTEND_MELSPEC_DB = 1    /* MelSpectrogram + AmplitudeToDB(top_db) + per-clip norm,
+                                          src/datasets/preprocessing.py:988-998,1013-1039        */
+} b200fbank_frontend;
+
+/*
+ * Options.  The first block is every keyword of torchaudio.compliance.kaldi.fbank
+ * (torchaudio/compliance/kaldi.py:514-541) except `waveform`, `channel` (the caller
+ * passes the selected channel), `dither` (must be 0: RNG parity is impossible) and
+ * `min_duration` (a host-side early-out, handled by the Python wrapper).  The second
+ * block is torchaudio.transforms.Resample (torchaudio/transforms/_transforms.py:945-979)
+ * as called by resample_waveform (src/datasets/preprocessing.py:61-76).
+ */
+typedef struct {
+  /* kaldi.fbank */
+  double blackman_coeff;            /* 0.42  */
+  double energy_floor;              /* 1.0   */
+  double frame_length;              /* 25.0 ms */
+  double frame_shift;               /* 10.0 ms */
+  double high_freq;                 /* 0.0   */
+  double low_freq;                  /* 20.0  */
+  double preemphasis_coefficient;   /* 0.97  */
+  double sample_frequency;          /* 16000.0 -- the rate the fbank runs at (resample target)  */
+  double vtln_high;                 /* -500.0 */
+  double vtln_low;                  /* 100.0 */
+  double vtln_warp;                 /* 1.0   */
+  int32_t num_mel_bins;             /* 23    */
+  int32_t window_type;              /* b200fbank_window, default POVEY                          */
+  int32_t htk_compat;               /* 0 */
+  int32_t raw_energy;               /* 1 */
+  int32_t remove_dc_offset;         /* 1 */
+  int32_t round_to_power_of_two;    /* 1 (0 is B200FBANK_ERR_UNSUPPORTED unless already 2^k)    */
+  int32_t snip_edges;               /* 1 */
+  int32_t subtract_mean;            /* 0 */
+  int32_t use_energy;               /* 0 */
+  int32_t use_log_fbank;            /* 1 */
+  int32_t use_power;                /* 1 */
+  /* Resample: input rates a clip may arrive at; rate_id indexes this table.  A rate equal
+     to sample_frequency means "no resampling" for that id. */
+  int32_t n_rates;                  /* 1..B200FBANK_MAX_RATES */
+  int32_t orig_rates[B200FBANK_MAX_RATES];
+  int32_t lowpass_filter_width;     /* 6    */
+  double rolloff;                   /* 0.99 */
+  /* frontend selector + MELSPEC_DB parameters (ignored for KALDI_FBANK) */
+  int32_t frontend;                 /* b200fbank_frontend */
+  int32_t n_fft;                    /* 1024 (AST_N_FFT, src/datasets/preprocessing.py:56)       */
+  int32_t hop_length;               /* 160  */
+  int32_t win_length;               /* 400  */
+  double top_db;                    /* 80.0; < 0 = None */
+} b200fbank_opts;
+
+typedef struct b200fbank_plan b200fbank_plan;
+
+int b200fbank_abi_version(void);
+
+/* Fill `o` with the defaults of kaldi.fbank (torchaudio/compliance/kaldi.py:514-541) and
+   Resample (torchaudio/transforms/_transforms.py:945-953); n_rates = 1, orig_rates[0] = 16000. */
+void b200fbank_default_opts(b200fbank_opts* o);
+
+/* Build the immutable tables (polyphase taps, window, twiddles, sparse mel weights) and,
+   when device >= 0, upload them.  device = -1 makes a host-only plan: table queries and
+   length arithmetic work, device calls return B200FBANK_ERR_NO_DEVICE.  Replaces the
+   per-call table construction of kaldi.fbank (get_mel_banks, kaldi.py:621-624;
+   _feature_window_function, :201) and Resample.__init__ (_transforms.py:969-979). */
+int b200fbank_plan_create(const b200fbank_opts* o, int device, b200fbank_plan** out);
+void b200fbank_plan_destroy(b200fbank_plan* p);
+const char* b200fbank_last_error(void);
+
+/* ---- host-side length arithmetic ------------------------------------------------- */
+/* ceil(new*n/orig), torchaudio/functional/functional.py:1427 */
+int64_t b200fbank_resampled_length(const b200fbank_plan* p, int64_t n_samples, int rate_id);
+/* frames produced for a clip of n_samples input samples at rate_id
+   (_get_strided, torchaudio/compliance/kaldi.py:63-69, after resampling) */
+int64_t b200fbank_num_frames(const b200fbank_plan* p, int64_t n_samples, int rate_id);
+/* num_mel_bins + use_energy */
+int b200fbank_num_cols(const b200fbank_plan* p);
+
+/* ---- table queries (host; used by the CPU test-suite to pin the host logic) -------- */
+typedef enum {
+  B200FBANK_TABLE_WINDOW = 0,       /* [window_size] float                                    */
+  B200FBANK_TABLE_MEL_DENSE = 1,    /* [num_mel_bins][padded/2] float (get_mel_banks layout)   */
+  B200FBANK_TABLE_TAPS_DENSE = 2    /* [new][2*width+orig] float for rate `arg`                */
+} b200fbank_table;
+/* Copies up to `cap` floats into dst; returns the table length in floats (or <0). */
+int64_t b200fbank_plan_table(const b200fbank_plan* p, int table, int arg, float* dst, int64_t cap);
+/* info[0..7] = window_shift, window_size, padded_window_size, n_rates, orig_reduced(arg),
+   new_reduced(arg), width(arg), taps_per_phase(arg) */
+int b200fbank_plan_info(const b200fbank_plan* p, int arg, int64_t info[8]);
+
+/* ---- device calls ---------------------------------------------------------------- */
+/*
+ * The fused path: resample -> frame -> DC removal -> pre-emphasis -> window -> real FFT
+ * -> power -> mel -> log-floor -> pad/crop to out_frames -> normalise -> SpecAugment
+ * zero-fill -> store (each output written once).  Replaces, per clip,
+ * ASTPreprocessor.preprocess (src/datasets/preprocessing.py:1013-1039),
+ * resample_waveform (:61-76), kaldi.fbank (torchaudio/compliance/kaldi.py:514-645) and
+ * ASTPreprocessor.apply_specaugment (:1075-1104) -- batched.
+ *
+ *  d_wav        concatenated mono float32 clips
+ *  d_offsets    [B+1] sample offsets into d_wav, or NULL for a dense (B, clip_samples) batch
+ *  clip_samples row length when d_offsets == NULL
+ *  d_rate_id    [B] index into orig_rates, or NULL (all clips at orig_rates[0])
+ *  d_masks      [B][4] = t_start, t_len, f_start, f_len (len 0 = none), or NULL; cells are
+ *               set to 0.0 AFTER normalisation (src/datasets/esc50.py:267-273)
+ *  d_mean/d_std [n_stats] with n_stats in {0, 1, n_cols}; 0 = no normalisation;
+ *               out = (x - mean) / std * target_std + target_mean
+ *               (src/datasets/preprocessing.py:1035-1037; north_star (x-mean)/(2*std))
+ *  d_out        (B, out_frames, n_cols) or (B, 1, n_cols, out_frames) float32; rows past a
+ *               clip's frame count hold 0.0 before normalisation
+ *  d_n_frames   [B] min(frames, out_frames) per clip, or NULL
+ */
+int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                      int64_t clip_samples, const int32_t* d_rate_id, int B,
+                      const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                      float target_mean, float target_std, int out_frames, int layout,
+                      float* d_out, int32_t* d_n_frames, void* stream);
+
+/* Dataset-statistics pass (north_star config 4; no reference code): the same fused path
+   with the epilogue replaced by float64 accumulation of per-column sum / sum of squares
+   over the REAL frames [0, min(frames, max_frames)) of every clip.  d_sums is
+   [2*n_cols + 1] doubles (sum, sumsq, frame count) and is ADDED to (zero it first).
+   The cross-GPU reduction is one all-reduce of d_sums (torch.distributed / NCCL). */
+int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                               int64_t clip_samples, const int32_t* d_rate_id, int B, int max_frames,
+                               double* d_sums, void* stream);
+
+/* Resample only: torchaudio.transforms.Resample(orig, sample_frequency)(wave) as called by
+   resample_waveform (src/datasets/preprocessing.py:61-76).  Output clip b is written at
+   d_out + (d_out_offsets ? d_out_offsets[b] : b * out_clip_samples). */
+int b200fbank_resample(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                       int64_t clip_samples, const int32_t* d_rate_id, int B, float* d_out,
+                       const int64_t* d_out_offsets, int64_t out_clip_samples, void* stream);
+
+/* Number of kernel launches the calls above issued on this thread since the last reset
+   (bench.py's gpu_launches claim). */
+int64_t b200fbank_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FBANK_H_ */
