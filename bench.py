@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/sec of 128-bin log-mel fbank per B200 (BASELINE.json metric).
+
+One "step" = one pass of the fused hot path over one batch of synthetic clips:
+``configs[1]`` of BASELINE.json -- 1024 ESC-50-shaped clips (5 s, 44.1 kHz mono float32)
+-> 16 kHz kaldi fbank (hanning, 128 mel, 10 ms hop) -> 512-frame target -> mean/std
+normalisation, float32.  Under torchrun every rank processes its own 1024 clips
+(weak scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+Prints ONE JSON line (rank 0).  ``value`` = device-resident throughput (CUDA events, max
+over ranks); ``e2e`` = same metric through the public API with HOST buffers (H2D of the
+waveforms and D2H of the features inside the timed region); ``roofline`` = algorithmic
+bytes / kernel time vs the measured HBM copy peak; ``cpu_baseline`` = the reference CPU
+path (torchaudio Resample + kaldi.fbank) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CLIP_SAMPLES = 220500          # 5 s @ 44.1 kHz
+CLIP_SECONDS = 5.0
+OUT_FRAMES = 512
+N_MELS = 128
+AST_MEAN, AST_STD = -6.6268, 5.0613      # SURVEY.md section 6 / BASELINE.md section 4
+METRIC = "audio-sec/sec log-mel fbank"
+UNIT = "audio-s/s"
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own path (torchaudio on host cores)
+# --------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One DataLoader-style worker: n clips through Resample -> kaldi.fbank -> pad -> norm."""
+    n, seed, kind = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(seed)
+    clips = [torch.rand(1, CLIP_SAMPLES, generator=g) * 2 - 1 for _ in range(min(n, 8))]
+    if kind == "reference":
+        import torchaudio.compliance.kaldi as kaldi
+        import torchaudio.transforms as T
+        rs = T.Resample(44100, 16000)
+
+        def one(w):
+            f = kaldi.fbank(rs(w), htk_compat=True, sample_frequency=16000, use_energy=False,
+                            window_type="hanning", num_mel_bins=128, dither=0.0, frame_shift=10)
+            f = torch.nn.functional.pad(f, (0, 0, 0, OUT_FRAMES - f.shape[0]))
+            return (f - AST_MEAN) / (2 * AST_STD)
+    else:
+        from oracle import fbank_oracle as O
+
+        def one(w):
+            return O.ast_frontend(w[0].numpy(), 44100, target_frames=OUT_FRAMES, mean=AST_MEAN, std=AST_STD)[0]
+    one(clips[0])                                     # warm the worker (imports, filter tables)
+    t0 = time.perf_counter()
+    for i in range(n):
+        one(clips[i % len(clips)])
+    return time.perf_counter() - t0
+
+
+def cpu_reference_throughput(clips_per_worker=300, workers=None):
+    """audio-s/s of the CPU path with `workers` single-thread processes (the reference's
+    DataLoader(num_workers) pattern, configs/base_training.yaml:104; workers are forked
+    like DataLoader workers, so call this BEFORE CUDA is initialised).  Returns dict."""
+    import multiprocessing as mp
+    import torch  # noqa: F401  (imported in the parent so forked workers inherit it)
+    try:
+        import torchaudio.compliance.kaldi  # noqa: F401
+        import torchaudio.transforms  # noqa: F401
+        kind = "reference"
+    except Exception:
+        kind = "port"
+    workers = workers or os.cpu_count() or 1
+    per = max(1, clips_per_worker)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        t_spawn = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        busy = pool.map(_cpu_worker, [(per, 1234 + i, kind) for i in range(workers)])
+        wall = time.perf_counter() - t1
+    # throughput over the slowest worker's compute time (excludes interpreter spawn + import)
+    t = max(busy)
+    n = per * workers
+    return dict(value=n * CLIP_SECONDS / t, unit=UNIT, cores=workers, kind=kind,
+                sample=f"{n} clips x 5 s @44.1 kHz ({per}/worker, {workers} single-thread worker processes; "
+                       f"slowest worker {t:.2f} s, pool wall {wall:.2f} s, spawn {t_spawn:.2f} s); "
+                       f"torchaudio Resample(44100,16000) + kaldi.fbank + pad 512 + (x-mean)/(2 std)"
+                       if kind == "reference" else
+                       f"{n} clips x 5 s via the numpy oracle port ({workers} workers)",
+                seconds=t, clips=n)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: 200 clips per worker per step (~1-2 s of host work per step)
+    workers = os.cpu_count() or 1
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference_throughput(200, workers)
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    t = sum(times) / len(times)
+    value = res["clips"] * CLIP_SECONDS / t
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"AST frontend, {res['clips']} ESC-50 clips (5 s @44.1 kHz) per step -> 16 kHz kaldi "
+                                     f"fbank 128 mel, 512-frame target, mean/std normalisation (bounded sample of the "
+                                     f"batch-1024 config)", l2="n/a (CPU)"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=res["cores"], kind=res["kind"], sample=res["sample"]),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_reference_throughput(300)           # before CUDA init: workers are forked
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    import torch
+    import torch.distributed as dist
+    import dl_sound_classification_b200 as b2
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    fe = b2.FbankFrontend(orig_rates=(44100,), device=dev, **b2.AST_FBANK_KWARGS)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wav = torch.rand((B, CLIP_SAMPLES), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    out = torch.empty((B, OUT_FRAMES, N_MELS), device=dev, dtype=torch.float32)
+    mean = torch.tensor([AST_MEAN], device=dev)
+    std = torch.tensor([AST_STD], device=dev)
+
+    def step():
+        fe(wav, out_frames=OUT_FRAMES, mean=mean, std=std, out=out, return_n_frames=False)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    b2.launch_count(reset=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
+    barrier()
+    launches = b2.launch_count()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if sampler:
+        time.sleep(0.1)
+        clocks = sampler.stop()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * CLIP_SECONDS * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API ----------------
+    h_wav = torch.empty((B, CLIP_SAMPLES), dtype=torch.float32).pin_memory()
+    h_wav.copy_(wav)
+    h_out = torch.empty((B, OUT_FRAMES, N_MELS), dtype=torch.float32).pin_memory()
+    d_wav2 = torch.empty_like(wav)
+
+    def e2e_step():
+        d_wav2.copy_(h_wav, non_blocking=True)
+        fe(d_wav2, out_frames=OUT_FRAMES, mean=mean, std=std, out=out, return_n_frames=False)
+        h_out.copy_(out, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * CLIP_SECONDS * e2e_steps / (float(t.item()) * 1e-3)
+    checksum = float(h_out[0, :498].double().sum())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg_bytes = B * (CLIP_SAMPLES * 4 + OUT_FRAMES * N_MELS * 4)
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32", data="synthetic",
+            config=dict(workload=f"AST frontend batch {B} ESC-50 clips (5 s @44.1 kHz mono f32) per GPU -> polyphase "
+                                 f"resample to 16 kHz -> kaldi fbank (hanning, 128 mel, 25/10 ms, 512-pt FFT) -> pad to "
+                                 f"512 frames -> (x-mean)/(2 std); BASELINE.json configs[1]",
+                        batch_per_gpu=B, clip_samples=CLIP_SAMPLES, out_frames=OUT_FRAMES, n_mels=N_MELS,
+                        l2=f"inputs {B * CLIP_SAMPLES * 4 / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)",
+                        kernel=os.environ.get("B200FBANK_KERNEL", "auto")),
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                          traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
+                          kernel_ms=k_ms),
+            cpu_baseline=cpu,
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * CLIP_SAMPLES * 4,
+                     d2h_bytes_per_step=B * OUT_FRAMES * N_MELS * 4, steps=e2e_steps, checksum=checksum),
+            gpu_launches=launches, clocks=clocks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

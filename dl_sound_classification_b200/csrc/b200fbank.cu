@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 #include "fbank_generic.cuh"
+#include "fbank_fast.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -128,9 +130,14 @@ struct b200fbank_plan {
   std::vector<float> twiddle;         // [padded/2][2]
   // device copies
   void* d_blob = nullptr;
+  std::vector<void*> owned;           // further device allocations
   b200::FbankParams base;             // table pointers + scalars filled once
   int generic_threads = 256;
   size_t generic_smem = 0;
+  // fast (AST-configuration) kernel
+  bool fast_ok = false;
+  b200::FastParams fast;
+  size_t fast_smem = 0;
 };
 
 namespace {
@@ -260,8 +267,114 @@ void generic_smem_layout(const b200fbank_plan* p, int F, int* sy, int* sx, int* 
   *sz = F * p->padded;
 }
 
+// Tables of the fast kernel (fbank_fast.cuh); leaves p->fast_ok = false when the
+// configuration is outside its envelope (the generic kernel then serves every call).
+int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
+  using namespace b200;
+  const b200fbank_opts& o = p->o;
+  p->fast_ok = false;
+  const char* env = getenv("B200FBANK_KERNEL");
+  if (env && strcmp(env, "generic") == 0) return 0;
+  if (!(p->size == FK_SIZE && p->shift == FK_SHIFT && p->padded == FK_N && o.snip_edges && !o.use_energy &&
+        p->n_mel <= 128))
+    return 0;
+  FastParams& f = p->fast;
+  memset(&f, 0, sizeof f);
+  f.fast_rate_id = -1;
+  std::vector<float> taps((size_t)FK_NG * FK_GROUP_FLOATS, 0.f);
+  std::vector<int> k0g(FK_NG, 0);
+  for (size_t ri = 0; ri < p->rates.size(); ++ri) {
+    const RateHost& r = p->rates[ri];
+    if (r.identity || r.orig != FK_ORIG || r.nw != FK_NEW || r.klen != FK_KLEN || r.width != FK_WIDTH) continue;
+    // group g = phases 5g..5g+4; phase r starts at dense index k0g + off(r) and keeps FK_LT taps
+    bool ok = true;
+    std::vector<int> first(r.nw), last(r.nw);
+    for (int ph = 0; ph < r.nw; ++ph) {
+      int a = r.klen, b = -1;
+      for (int k = 0; k < r.klen; ++k)
+        if (std::fabs(r.dense[(size_t)ph * r.klen + k]) > 1e-25f) { a = std::min(a, k); b = std::max(b, k); }
+      first[ph] = a; last[ph] = b;
+    }
+    for (int g = 0; g < FK_NG && ok; ++g) {
+      int k0 = r.klen;
+      for (int q = 0; q < FK_RP; ++q) k0 = std::min(k0, first[FK_RP * g + q] - fk_off(q));
+      k0 = std::max(k0, 0);
+      k0g[g] = k0;
+      for (int q = 0; q < FK_RP; ++q) {
+        const int s0 = k0 + fk_off(q);
+        if (s0 > first[FK_RP * g + q] || last[FK_RP * g + q] >= s0 + FK_LT) ok = false;
+      }
+      int e = 0;
+      for (int u = 0; u < FK_WIN; ++u)
+        for (int q = 0; q < FK_RP; ++q) {
+          const int j = u - fk_off(q);
+          if (j < 0 || j >= FK_LT) continue;
+          const int k = k0 + u;
+          taps[(size_t)g * FK_GROUP_FLOATS + e++] = (k < r.klen) ? r.dense[(size_t)(FK_RP * g + q) * r.klen + k] : 0.f;
+        }
+      if (e != FK_RP * FK_LT) ok = false;
+    }
+    if (ok) f.fast_rate_id = (int)ri;
+  }
+  // stage-1 twiddles W_512^(k1 * lane)
+  std::vector<float> tw(512 * 2);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double a = -2.0 * M_PI * (double)(k1 * l) / 512.0;
+      tw[2 * (k1 * 32 + l)] = (float)std::cos(a);
+      tw[2 * (k1 * 32 + l) + 1] = (float)std::sin(a);
+    }
+  // mel weights, lanes = bins
+  f.mel_groups = (p->n_mel + 31) / 32;
+  int rows = 0;
+  for (int i = 0; i < f.mel_groups; ++i) {
+    int mc = 0;
+    for (int m = 32 * i; m < std::min(p->n_mel, 32 * i + 32); ++m) mc = std::max(mc, p->mel_cnt[m]);
+    f.mel_maxcnt[i] = mc; f.mel_woff[i] = rows; rows += mc;
+  }
+  f.mel_rows = rows;
+  std::vector<float> melw((size_t)std::max(rows, 1) * 32, 0.f);
+  for (int i = 0; i < f.mel_groups; ++i)
+    for (int j = 0; j < f.mel_maxcnt[i]; ++j)
+      for (int l = 0; l < 32; ++l) {
+        const int m = 32 * i + l;
+        if (m < p->n_mel && j < p->mel_cnt[m]) melw[(size_t)(f.mel_woff[i] + j) * 32 + l] = p->mel_w[p->mel_off[m] + j];
+      }
+  for (size_t ri = 0; ri < p->rates.size(); ++ri) {
+    const RateHost& r = p->rates[ri];
+    int part = FK_RING_HOPS * FK_SHIFT;
+    if (!r.identity) {
+      // largest staging pass whose input tile fits the x region
+      while (part > 32 && ((int64_t)(part / r.nw + 2) * r.orig + r.klen) > FK_XFLOATS - 4) part -= 32;
+      if (((int64_t)(part / r.nw + 2) * r.orig + r.klen) > FK_XFLOATS - 4) return 0;   // ratio too extreme
+    }
+    f.gen_part[ri] = part;
+  }
+  p->fast_smem = (size_t)(FK_XFLOATS + FK_RING_FLOATS + FK_NG * FK_GROUP_FLOATS + 1024 + rows * 32) * 4;
+  if (p->fast_smem > 113 * 1024) return 0;
+  auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    CUDA_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    *dst = d;
+    return 0;
+  };
+  if (int rc = dev_copy(taps.data(), taps.size() * 4, (const void**)&f.taps)) return rc;
+  if (int rc = dev_copy(k0g.data(), k0g.size() * 4, (const void**)&f.k0g)) return rc;
+  if (int rc = dev_copy(tw.data(), tw.size() * 4, (const void**)&f.tw)) return rc;
+  if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
+  const char* seg = getenv("B200FBANK_SEG");
+  f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 128;
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast_smem));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast_smem));
+  p->fast_ok = true;
+  return 0;
+}
+
 int upload(b200fbank_plan* p) {
   CUDA_TRY(cudaSetDevice(p->device));
+  std::vector<void*>& blob_host_extra = p->owned;
   // one blob: [window][twiddle][mel_w][mel_start][mel_cnt][mel_off]{[taps][k0]}*
   std::vector<char> blob;
   auto put = [&](const void* src, size_t bytes) {
@@ -303,6 +416,8 @@ int upload(b200fbank_plan* p) {
   k.n_mel = p->n_mel; k.n_cols = p->n_cols;
   k.mel_start = (const int*)(d + o_ms); k.mel_cnt = (const int*)(d + o_mc); k.mel_off = (const int*)(d + o_mo);
   k.mel_w = (const float*)(d + o_mw);
+
+  if (int rc = setup_fast(p, blob_host_extra)) return rc;
 
   // pick the largest tile that fits comfortably (two CTAs per SM when possible)
   int F = 16;
@@ -366,6 +481,7 @@ int b200fbank_plan_create(const b200fbank_opts* o, int device, b200fbank_plan** 
 void b200fbank_plan_destroy(b200fbank_plan* p) {
   if (!p) return;
   if (p->d_blob) cudaFree(p->d_blob);
+  for (void* d : p->owned) cudaFree(d);
   delete p;
 }
 
@@ -433,10 +549,18 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   k.target_mean = target_mean; k.target_std = target_std;
   const bool cms = p->o.subtract_mean != 0;
   if (cms) { k.masks = nullptr; k.n_stats = 0; }     // raw features first, cms_kernel finishes
-  k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
-  const int64_t grid = (int64_t)B * k.tiles;
-  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles = %lld exceeds the grid limit", (long long)grid);
-  b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
+  if (p->fast_ok) {
+    b200::FastParams f = p->fast;
+    f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
+    const int64_t grid = (int64_t)B * f.segs;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
+    b200::fbank_fast_kernel<false><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, st>>>(k, f);
+  } else {
+    k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
+    const int64_t grid = (int64_t)B * k.tiles;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles = %lld exceeds the grid limit", (long long)grid);
+    b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (cms) {
@@ -461,10 +585,18 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
   b200::FbankParams k = p->base;
   k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
   k.max_frames = max_frames; k.sums = d_sums;
-  k.tiles = (max_frames + k.tile_frames - 1) / k.tile_frames;
-  const int64_t grid = (int64_t)B * k.tiles;
-  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
-  b200::fbank_generic_kernel<true><<<(unsigned)grid, p->generic_threads, p->generic_smem, (cudaStream_t)stream>>>(k);
+  if (p->fast_ok) {
+    b200::FastParams f = p->fast;
+    f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
+    const int64_t grid = (int64_t)B * f.segs;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
+    b200::fbank_fast_kernel<true><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, (cudaStream_t)stream>>>(k, f);
+  } else {
+    k.tiles = (max_frames + k.tile_frames - 1) / k.tile_frames;
+    const int64_t grid = (int64_t)B * k.tiles;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+    b200::fbank_generic_kernel<true><<<(unsigned)grid, p->generic_threads, p->generic_smem, (cudaStream_t)stream>>>(k);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -9,6 +9,7 @@
 
 #define B200_MAX_RATES 8
 #define B200_FLT_EPSILON 1.1920928955078125e-07f   // torchaudio/compliance/kaldi.py:26
+#define B200_LOG_FLT_EPSILON -15.942384719848633f  // float32(log(FLT_EPSILON))
 
 namespace b200 {
 

@@ -1,0 +1,405 @@
+// Tuned fused kernel for the AST configuration: 25 ms / 10 ms frames at 16 kHz (400 / 160
+// samples), 512-point FFT, up to 128 mel bins, snip_edges, no energy column.
+//
+// One CTA (256 threads, 2 CTAs per SM) streams a segment of one clip in chunks of 32 frames:
+//
+//   load      input chunk -> smem (float4 when 16-B aligned), zero-filled outside the clip
+//   resample  44.1 kHz -> 16 kHz polyphase FIR: lanes = 32 hops (smem stride 441, odd ->
+//             conflict-free), warps = groups of 5 phases whose 175 taps are broadcast from
+//             smem as float4; 16 kHz samples go to a 34-hop ring (hop stride 161) and never
+//             touch HBM.  Other rates use a per-sample loop into the same ring.
+//   FFT       each warp takes 4 frames: DC removal + pre-emphasis + window on load, two
+//             frames packed into one complex 512-point transform = radix-16 in registers ->
+//             XOR-swizzled smem transpose -> radix-32 in registers; conjugate split by warp
+//             shuffle; |.|^2
+//   mel       lanes = mel bins, sparse triangular weights from smem, log, normalise,
+//             SpecAugment zero-fill, coalesced store (each output written once).
+#pragma once
+#include "common.cuh"
+#include "fbank_generic.cuh"
+#include "fft_regs.cuh"
+
+namespace b200 {
+
+constexpr int FK_THREADS = 256;
+constexpr int FK_CH = 32;                 // frames (= 16 kHz hops) per chunk
+constexpr int FK_SIZE = 400, FK_SHIFT = 160, FK_N = 512;
+constexpr int FK_RP = 5;                  // phases per group
+constexpr int FK_NG = 32;                 // groups: 160 phases
+constexpr int FK_LT = 35;                 // taps kept per phase (34 non-zero + alignment slack)
+constexpr int FK_WIN = 45;                // input samples one lane reads per group
+constexpr int FK_GROUP_FLOATS = 176;      // 175 taps in consumption order, padded to float4
+constexpr int FK_ORIG = 441, FK_NEW = 160, FK_KLEN = 475, FK_WIDTH = 17;
+constexpr int FK_RING_STRIDE = 161;       // hop stride in the ring: odd -> conflict-free column stores
+constexpr int FK_RING_HOPS = 34;
+constexpr int FK_RING_FLOATS = 5476;      // 34 * 161 = 5474, padded to a multiple of 4
+constexpr int FK_EBUF = 1056;             // floats per warp: 512 complex (exchange) / 4 x 264 (power)
+constexpr int FK_PSTRIDE = 264;
+constexpr int FK_XFLOATS = 15040;         // 33 * 441 + 475 + slack, multiple of 4
+
+__host__ __device__ constexpr int fk_off(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 7 : 10; }
+
+struct FastParams {
+  const float* taps;      // [32][176] consumption-ordered taps of the 441 -> 160 resampler
+  const int* k0g;         // [32] first input index (dense tap coordinates) of each group
+  int fast_rate_id;       // index in the rate table that is 44100 -> 16000, or -1
+  const float2* tw;       // [16][32]  W_512^(k1 * lane)
+  const float* melw;      // [sum maxcnt][32] zero-padded weights, lanes = bins
+  int mel_groups;         // ceil(n_mel / 32)
+  int mel_maxcnt[4];      // longest filter in each group of 32 bins
+  int mel_woff[4];        // row offset of each group in melw
+  int mel_rows;           // sum of mel_maxcnt
+  int gen_part[B200_MAX_RATES];   // outputs per staging pass for rates on the per-sample path
+  int seg_frames, segs;
+};
+
+// Copy x[in_lo, in_lo + nx) of the clip into A[sh + i]; returns sh (0..3), chosen so that
+// 16-B aligned global addresses land on 16-B aligned shared addresses.
+__device__ __forceinline__ int fk_load_x(const ClipInfo& c, int64_t in_lo, int nx, float* A) {
+  const int tid = threadIdx.x;
+  const float* g = c.wav + in_lo;
+  const int sh = (int)(((uintptr_t)g >> 2) & 3);
+  float* d = A + sh;
+  int head = (4 - sh) & 3;
+  if (head > nx) head = nx;
+  if (tid < head) {
+    int64_t s = in_lo + tid;
+    d[tid] = (s >= 0 && s < c.n_in) ? __ldg(g + tid) : 0.f;
+  }
+  const int nvec = (nx - head) >> 2;
+  for (int v = tid; v < nvec; v += FK_THREADS) {
+    const int i = head + 4 * v;
+    const int64_t s = in_lo + i;
+    float4 x;
+    if (s >= 0 && s + 3 < c.n_in) {
+      x = __ldg(reinterpret_cast<const float4*>(g + i));
+    } else {
+      x.x = (s >= 0 && s < c.n_in) ? __ldg(g + i) : 0.f;
+      x.y = (s + 1 >= 0 && s + 1 < c.n_in) ? __ldg(g + i + 1) : 0.f;
+      x.z = (s + 2 >= 0 && s + 2 < c.n_in) ? __ldg(g + i + 2) : 0.f;
+      x.w = (s + 3 >= 0 && s + 3 < c.n_in) ? __ldg(g + i + 3) : 0.f;
+    }
+    *reinterpret_cast<float4*>(d + i) = x;
+  }
+  const int tail = head + 4 * nvec + tid;
+  if (tail < nx) {
+    int64_t s = in_lo + tail;
+    d[tail] = (s >= 0 && s < c.n_in) ? __ldg(g + tail) : 0.f;
+  }
+  return sh;
+}
+
+// Per-sample polyphase loop (any rate): resampled samples [s0, s0 + count) -> ring, where
+// ring sample 0 is absolute resampled index ring_base.  xs[i] = x[in_lo + i].
+__device__ __forceinline__ void fk_resample_generic(const RateDev& R, const float* xs, int64_t in_lo,
+                                                    int64_t s0, int count, float* ring, int64_t ring_base) {
+  for (int t = threadIdx.x; t < count; t += FK_THREADS) {
+    const int64_t s = s0 + t;
+    const int64_t q = s / R.nw;
+    const int ph = (int)(s - q * R.nw);
+    const float* tp = R.taps + (size_t)ph * R.L;
+    const float* x = xs + (q * R.orig + __ldg(R.k0 + ph) - R.width - in_lo);
+    float acc = 0.f;
+    for (int j = 0; j < R.L; ++j) acc = fmaf(__ldg(tp + j), x[j], acc);
+    const int rel = (int)(s - ring_base);
+    ring[rel + rel / FK_SHIFT] = acc;
+  }
+}
+
+// One resampler task: 5 phases x 32 hops (lane = hop).  T4 = the group's 44 float4 of taps in
+// consumption order, xs = this lane's first input sample, yo = ring slot of phase 5g of this hop.
+__device__ __forceinline__ void fk_resample_group(const float4* __restrict__ T4, const float* __restrict__ xs,
+                                                  float* __restrict__ yo) {
+  float acc[FK_RP];
+#pragma unroll
+  for (int r = 0; r < FK_RP; ++r) acc[r] = 0.f;
+  float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e = 0;
+#pragma unroll
+  for (int u = 0; u < FK_WIN; ++u) {
+    const float xv = xs[u];
+#pragma unroll
+    for (int r = 0; r < FK_RP; ++r) {
+      const int j = u - fk_off(r);
+      if (j >= 0 && j < FK_LT) {
+        if ((e & 3) == 0) cur = T4[e >> 2];
+        const float tap = (e & 3) == 0 ? cur.x : (e & 3) == 1 ? cur.y : (e & 3) == 2 ? cur.z : cur.w;
+        acc[r] = fmaf(tap, xv, acc[r]);
+        ++e;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < FK_RP; ++r) yo[r] = acc[r];
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankParams p, const FastParams fp) {
+  extern __shared__ __align__(16) float smem[];
+  float* A = smem;                                   // [FK_XFLOATS] input chunk, later per-warp exchange / power
+  float* ring = A + FK_XFLOATS;                      // [FK_RING_FLOATS] 16 kHz samples, 34 hops x 161
+  float* staps = ring + FK_RING_FLOATS;              // [32 * 176]
+  float2* stw = reinterpret_cast<float2*>(staps + FK_NG * FK_GROUP_FLOATS);   // [512]
+  float* smelw = reinterpret_cast<float*>(stw + 512);                         // [mel_rows * 32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / fp.segs;
+  const int seg = blockIdx.x - b * fp.segs;
+  const ClipInfo c = clip_info(p, b);
+  const int cap = STATS ? p.max_frames : p.out_frames;
+  const int m_eff = (int)(c.m < cap ? c.m : cap);
+  const int row_begin = seg * fp.seg_frames;
+  if (row_begin >= cap) return;
+  const int row_end = (row_begin + fp.seg_frames < cap) ? row_begin + fp.seg_frames : cap;
+  if (!STATS && seg == 0 && tid == 0 && p.n_frames_out) p.n_frames_out[b] = m_eff;
+  if (STATS && row_begin >= m_eff) return;
+
+  const int rid = p.rate_id ? p.rate_id[b] : 0;
+  const bool fast = (rid == fp.fast_rate_id);
+
+  // ---- one-time staging of the tables -------------------------------------------------------
+  if (row_begin < m_eff) {
+    if (fast) {
+      const float4* src = reinterpret_cast<const float4*>(fp.taps);
+      float4* dst = reinterpret_cast<float4*>(staps);
+      for (int i = tid; i < FK_NG * FK_GROUP_FLOATS / 4; i += FK_THREADS) dst[i] = __ldg(src + i);
+    }
+    for (int i = tid; i < 512; i += FK_THREADS) stw[i] = __ldg(fp.tw + i);
+    for (int i = tid; i < fp.mel_rows * 32; i += FK_THREADS) smelw[i] = __ldg(fp.melw + i);
+  }
+  float win[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
+  int mstart[4];
+  float nmean[4], nscale[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = lane + 32 * i;
+    mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
+    nmean[i] = 0.f; nscale[i] = 1.f;
+    if (!STATS && p.n_stats > 0 && m < p.n_mel) {
+      const int si = p.n_stats == 1 ? 0 : m;
+      nmean[i] = __ldg(p.mean + si);
+      nscale[i] = p.target_std / __ldg(p.std + si);
+    }
+  }
+  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+  if (!STATS && p.masks) {
+    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+  }
+  const float dc_on = p.remove_dc ? 1.f : 0.f;
+  double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
+  __syncthreads();
+
+  bool ring_valid = false;
+  for (int r0 = row_begin; r0 < row_end; r0 += FK_CH) {
+    int nf = m_eff - r0;
+    nf = nf < 0 ? 0 : (nf > FK_CH ? FK_CH : nf);
+    if (nf > 0) {
+      // ================= resample: fill ring hops [hop_lo, 34) =============================
+      const int hop_lo = ring_valid ? 2 : 0;
+      if (ring_valid) {          // carry the last two hops to the front
+        float keep0 = 0.f, keep1 = 0.f;
+        if (tid < 2 * FK_RING_STRIDE) keep0 = ring[32 * FK_RING_STRIDE + tid];
+        if (tid + FK_THREADS < 2 * FK_RING_STRIDE) keep1 = ring[32 * FK_RING_STRIDE + tid + FK_THREADS];
+        __syncthreads();
+        if (tid < 2 * FK_RING_STRIDE) ring[tid] = keep0;
+        if (tid + FK_THREADS < 2 * FK_RING_STRIDE) ring[tid + FK_THREADS] = keep1;
+      }
+      const int64_t ring_base = (int64_t)r0 * FK_SHIFT;          // absolute index of ring sample 0
+      if (fast) {
+        const int64_t in_lo = (int64_t)(r0 + hop_lo) * FK_ORIG - FK_WIDTH;
+        const int nx = (FK_RING_HOPS - hop_lo - 1) * FK_ORIG + FK_KLEN + 8;
+        const int sh = fk_load_x(c, in_lo, nx, A);
+        __syncthreads();
+        const float* xs = A + sh;
+        if (!ring_valid)       // prologue: hops 0 and 1 on the per-sample path
+          fk_resample_generic(c.R, xs, in_lo, ring_base, 2 * FK_SHIFT, ring, ring_base);
+        const float* xl = xs + (ring_valid ? 0 : 2 * FK_ORIG) + lane * FK_ORIG;
+        float* yl = ring + (2 + lane) * FK_RING_STRIDE;
+#pragma unroll 1
+        for (int gi = 0; gi < FK_NG / 8; ++gi) {
+          const int g = warp * (FK_NG / 8) + gi;
+          fk_resample_group(reinterpret_cast<const float4*>(staps + g * FK_GROUP_FLOATS),
+                            xl + __ldg(fp.k0g + g), yl + FK_RP * g);
+        }
+      } else if (c.R.identity) {
+        const int cnt = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
+        const int64_t s0 = ring_base + hop_lo * FK_SHIFT;
+        for (int t = tid; t < cnt; t += FK_THREADS) {
+          const int64_t s = s0 + t;
+          const int rel = (int)(s - ring_base);
+          ring[rel + rel / FK_SHIFT] = (s < c.n_in) ? __ldg(c.wav + s) : 0.f;
+        }
+      } else {
+        const int total = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
+        const int part = fp.gen_part[rid];
+        for (int done = 0; done < total; done += part) {
+          const int cnt = (total - done < part) ? total - done : part;
+          const int64_t s0 = ring_base + hop_lo * FK_SHIFT + done;
+          const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
+          const int64_t in_lo = q_lo * c.R.orig - c.R.width;
+          const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
+          if (done > 0) __syncthreads();
+          const int sh = fk_load_x(c, in_lo, nx, A);
+          __syncthreads();
+          fk_resample_generic(c.R, A + sh, in_lo, s0, cnt, ring, ring_base);
+        }
+      }
+      __syncthreads();
+      ring_valid = true;
+    }
+
+    // ================= FFT + mel: warp w owns frames 4w .. 4w+3 of the chunk ===============
+    const int f0 = 4 * warp;
+    float* Pw = A + warp * FK_EBUF;
+    const bool any_live = f0 < nf;
+    if (any_live) {
+      float2 z1[16], z2[16];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const bool live = (f0 + h) < nf;
+        const float* yb = ring + (f0 + h) * FK_RING_STRIDE + lane;
+        float yv[13], s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+          const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+          const bool ok = live && (j < 12 || lane < 16);
+          yv[j] = ok ? yb[off] : 0.f;
+          s += yv[j];
+        }
+        const float mean = warp_sum(s) * (dc_on / (float)FK_SIZE);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+          const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+          const bool ok = live && (j < 12 || lane < 16);
+          float prev;
+          if (j == 0) {
+            const float pv = ok ? yb[lane == 0 ? off : off - 1] : 0.f;   // replicate pad at the frame start
+            prev = pv;
+          } else if (j == 5 || j == 10) {
+            prev = ok ? yb[lane == 0 ? off - 2 : off - 1] : 0.f;          // previous sample sits in the previous hop row
+          } else {
+            prev = ok ? yb[off - 1] : 0.f;
+          }
+          const float v = ((yv[j] - mean) - p.preemph * (prev - mean)) * win[j];
+          if (h == 0) z1[j].x = v; else if (h == 1) z1[j].y = v; else if (h == 2) z2[j].x = v; else z2[j].y = v;
+        }
+      }
+#pragma unroll
+      for (int j = 13; j < 16; ++j) { z1[j] = make_float2(0.f, 0.f); z2[j] = make_float2(0.f, 0.f); }
+
+      // ---- stage 1: 16-point DFT over n1 (n = lane + 32 n1), twiddle W_512^(lane * k1) ----
+      fft_dif<16>(z1);
+      fft_dif<16>(z2);
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) {
+        const float2 w = stw[k1 * 32 + lane];
+        constexpr int dummy = 0; (void)dummy;
+        const int slot = bitrev_n(k1, 4);
+        const float2 a = z1[slot], bq = z2[slot];
+        z1[slot] = make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+        z2[slot] = make_float2(fmaf(-bq.y, w.y, bq.x * w.x), fmaf(bq.y, w.x, bq.x * w.y));
+      }
+
+      // ---- exchange through smem (XOR swizzle), one transform at a time ---------------------
+      float2* E = reinterpret_cast<float2*>(Pw);
+      float2 u[32];
+      const int k1l = lane & 15;
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) E[k1 * 32 + (lane ^ k1)] = z1[bitrev_n(k1, 4)];
+      __syncwarp();
+      if (lane < 16) {
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) u[n2] = E[k1l * 32 + (n2 ^ k1l)];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) E[k1 * 32 + (lane ^ k1)] = z2[bitrev_n(k1, 4)];
+      __syncwarp();
+      if (lane >= 16) {
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) u[n2] = E[k1l * 32 + (n2 ^ k1l)];
+      }
+      __syncwarp();
+
+      // ---- stage 2: 32-point DFT over n2; lane = k1 + 16 * transform ------------------------
+      fft_dif<32>(u);
+
+      // ---- split the two real spectra (Z[k], conj Z[512-k]) and take |.|^2 ------------------
+      const int src = ((16 - k1l) & 15) | (lane & 16);
+      const int prow = (lane >> 4) * 2 * FK_PSTRIDE + k1l;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float2 zk = u[bitrev_n(k2, 5)];
+        const float2 own = u[bitrev_n((32 - k2) & 31, 5)];
+        const float2 oth = u[bitrev_n(31 - k2, 5)];
+        float px = __shfl_sync(0xffffffffu, oth.x, src);
+        float py = __shfl_sync(0xffffffffu, oth.y, src);
+        if (k1l == 0) { px = own.x; py = own.y; }
+        const float ar = zk.x + px, ai = zk.y - py, br = zk.y + py, bi = px - zk.x;
+        float pa = 0.25f * fmaf(ar, ar, ai * ai), pb = 0.25f * fmaf(br, br, bi * bi);
+        if (!p.use_power) { pa = sqrtf(pa); pb = sqrtf(pb); }
+        Pw[prow + 16 * k2] = pa;
+        Pw[prow + FK_PSTRIDE + 16 * k2] = pb;
+      }
+      __syncwarp();
+    }
+
+    // ---- mel (lanes = bins), log, epilogue, store ---------------------------------------------
+    for (int i = 0; i < fp.mel_groups; ++i) {
+      const int m = lane + 32 * i;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (any_live) {
+        const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
+        const int st = mstart[i];
+        const int mc = fp.mel_maxcnt[i];
+        for (int j = 0; j < mc; ++j) {
+          const float w = wrow[j * 32];
+          int kk = st + j;
+          kk = kk > 255 ? 255 : kk;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) acc[h] = fmaf(w, Pw[h * FK_PSTRIDE + kk], acc[h]);
+        }
+      }
+      if (m < p.n_mel) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int t = r0 + f0 + h;
+          const bool live = (f0 + h) < nf;
+          float x = acc[h];
+          if (p.use_log) x = x > B200_FLT_EPSILON ? __logf(x) : B200_LOG_FLT_EPSILON;   // exact floor value (kaldi.py:633)
+          if (STATS) {
+            if (live) { st_s[i] += (double)x; st_ss[i] += (double)x * (double)x; }
+          } else if (t < row_end) {
+            x = live ? x : 0.f;
+            x = fmaf(x - nmean[i], nscale[i], p.n_stats > 0 ? p.target_mean : 0.f);
+            if ((t >= mk0 && t < mk0 + mk1) || (m >= mk2 && m < mk2 + mk3)) x = 0.f;
+            if (p.layout == 0) p.out[((size_t)b * p.out_frames + t) * p.n_cols + m] = x;
+            else p.out[((size_t)b * p.n_cols + m) * p.out_frames + t] = x;
+          }
+        }
+      }
+    }
+    __syncthreads();      // A (exchange / power) and the ring are reused by the next chunk
+  }
+
+  if (STATS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = lane + 32 * i;
+      if (i < fp.mel_groups && m < p.n_mel) {
+        atomicAdd(p.sums + m, st_s[i]);
+        atomicAdd(p.sums + p.n_cols + m, st_ss[i]);
+      }
+    }
+    if (tid == 0) {
+      int real = m_eff - row_begin;
+      real = real > (row_end - row_begin) ? (row_end - row_begin) : real;
+      if (real > 0) atomicAdd(p.sums + 2 * p.n_cols, (double)real);
+    }
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,101 @@
+// In-register radix-2 DIF FFTs (N = 2..32) with compile-time twiddles.
+//
+// Everything is a fully unrolled template over a float2 array held in registers; twiddles
+// are float literals rounded from float64 (cos/sin of multiples of 2*pi/32), and rotations by
+// multiples of pi/2 and pi/4 are special-cased so no multiply by 0 or 1 is ever issued.
+// The same code compiles for the host (tests/host_fft_check.cpp) so the index arithmetic of
+// the warp-level 512-point transform is pinned on the CPU test-suite.
+#pragma once
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_CHD __host__ __device__
+#else
+#include <cmath>
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#define B200_HD inline
+#define B200_CHD
+#endif
+
+namespace b200 {
+
+// cos(2*pi*k/32), k = 0..8, rounded from float64
+template <int K> struct Cos32;
+template <> struct Cos32<0> { static constexpr float v = 1.0f; };
+template <> struct Cos32<1> { static constexpr float v = 0.98078528040323043f; };
+template <> struct Cos32<2> { static constexpr float v = 0.92387953251128674f; };
+template <> struct Cos32<3> { static constexpr float v = 0.83146961230254524f; };
+template <> struct Cos32<4> { static constexpr float v = 0.70710678118654752f; };
+template <> struct Cos32<5> { static constexpr float v = 0.55557023301960218f; };
+template <> struct Cos32<6> { static constexpr float v = 0.38268343236508977f; };
+template <> struct Cos32<7> { static constexpr float v = 0.19509032201612825f; };
+template <> struct Cos32<8> { static constexpr float v = 0.0f; };
+
+// cos / sin of 2*pi*K/32 for K in [0, 32) via quadrant symmetry
+template <int K> struct CS32 {
+  static constexpr int k = ((K % 32) + 32) % 32;
+  static constexpr int q = k / 8, r = k % 8;
+  // angle = q*90deg + r*11.25deg
+  static constexpr float c0 = Cos32<r>::v, s0 = Cos32<8 - r>::v;   // cos, sin of the residual
+  static constexpr float c = (q == 0) ? c0 : (q == 1) ? -s0 : (q == 2) ? -c0 : s0;
+  static constexpr float s = (q == 0) ? s0 : (q == 1) ? c0 : (q == 2) ? -s0 : -c0;
+};
+
+// a * exp(-2*pi*i * K / 32)
+template <int K> B200_HD float2 mul_w32(float2 a) {
+  constexpr int k = ((K % 32) + 32) % 32;
+  if constexpr (k == 0) return a;
+  else if constexpr (k == 8) return make_float2(a.y, -a.x);
+  else if constexpr (k == 16) return make_float2(-a.x, -a.y);
+  else if constexpr (k == 24) return make_float2(-a.y, a.x);
+  else if constexpr (k == 4) { constexpr float h = Cos32<4>::v; return make_float2((a.x + a.y) * h, (a.y - a.x) * h); }
+  else if constexpr (k == 12) { constexpr float h = Cos32<4>::v; return make_float2((a.y - a.x) * h, -(a.x + a.y) * h); }
+  else if constexpr (k == 20) { constexpr float h = Cos32<4>::v; return make_float2(-(a.x + a.y) * h, (a.x - a.y) * h); }
+  else if constexpr (k == 28) { constexpr float h = Cos32<4>::v; return make_float2((a.x - a.y) * h, (a.x + a.y) * h); }
+  else {
+    constexpr float c = CS32<k>::c, s = CS32<k>::s;
+    // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+#ifdef __CUDA_ARCH__
+    return make_float2(fmaf(a.y, s, a.x * c), fmaf(-a.x, s, a.y * c));
+#else
+    return make_float2(std::fmaf(a.y, s, a.x * c), std::fmaf(-a.x, s, a.y * c));
+#endif
+  }
+}
+
+template <int N> struct BitRev;   // bit reversal of I over log2(N) bits
+template <int N, int I> struct BitRevI {
+  static constexpr int bits = (N == 2) ? 1 : (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
+  static constexpr int rev(int i) { int r = 0; for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b); return r; }
+  static constexpr int v = rev(I);
+};
+B200_CHD constexpr int bitrev_n(int i, int bits) { int r = 0; for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b); return r; }
+B200_CHD constexpr int log2_n(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
+
+// One DIF stage: blocks of size 2*H starting at BASE; twiddle step = 32 / (2*H).
+template <int N, int H, int BASE, int J> struct DifButterfly {
+  static B200_HD void run(float2 (&v)[N]) {
+    float2 a = v[BASE + J], b = v[BASE + J + H];
+    v[BASE + J] = make_float2(a.x + b.x, a.y + b.y);
+    v[BASE + J + H] = mul_w32<J * (16 / H)>(make_float2(a.x - b.x, a.y - b.y));
+    if constexpr (J + 1 < H) DifButterfly<N, H, BASE, J + 1>::run(v);
+  }
+};
+template <int N, int H, int BASE> struct DifBlocks {
+  static B200_HD void run(float2 (&v)[N]) {
+    DifButterfly<N, H, BASE, 0>::run(v);
+    if constexpr (BASE + 2 * H < N) DifBlocks<N, H, BASE + 2 * H>::run(v);
+  }
+};
+template <int N, int H> struct DifStages {
+  static B200_HD void run(float2 (&v)[N]) {
+    DifBlocks<N, H, 0>::run(v);
+    if constexpr (H > 1) DifStages<N, H / 2>::run(v);
+  }
+};
+
+// In-place forward DFT of N points (N in {2,4,8,16,32}); X[k] ends up in v[bitrev(k)].
+template <int N> B200_HD void fft_dif(float2 (&v)[N]) { DifStages<N, N / 2>::run(v); }
+
+}  // namespace b200
