@@ -21,6 +21,10 @@
 
 namespace {
 
+// The opt-in limit is a per-function attribute shared by every plan in the process, so it is
+// always raised to the sm_100 maximum (227 KB); occupancy depends on the launch size only.
+constexpr int kMaxSmemOptin = 227 * 1024;
+
 thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
 
@@ -350,7 +354,8 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     }
     f.gen_part[ri] = part;
   }
-  p->fast_smem = (size_t)(FK_XFLOATS + FK_RING_FLOATS + FK_NG * FK_GROUP_FLOATS + 1024 + rows * 32) * 4;
+  p->fast_smem = (size_t)(FK_ATFLOATS + FK_RING_FLOATS + 1024 + rows * 32) * 4;
+  f.ast_bank = (f.mel_groups == 4 && f.mel_maxcnt[0] == 2 && f.mel_maxcnt[1] == 3 && f.mel_maxcnt[2] == 6 && f.mel_maxcnt[3] == 11);
   if (p->fast_smem > 113 * 1024) return 0;
   auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {
     void* d = nullptr;
@@ -366,8 +371,10 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
   const char* seg = getenv("B200FBANK_SEG");
   f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 128;
-  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast_smem));
-  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast_smem));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   p->fast_ok = true;
   return 0;
 }
@@ -432,8 +439,8 @@ int upload(b200fbank_plan* p) {
     }
   }
   if (F < 2) return fail(B200FBANK_ERR_UNSUPPORTED, "configuration does not fit in shared memory");
-  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->generic_smem));
-  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->generic_smem));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   return 0;
 }
 
@@ -554,7 +561,8 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
-    b200::fbank_fast_kernel<false><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, st>>>(k, f);
+    if (f.ast_bank) b200::fbank_fast_kernel<false, true><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, st>>>(k, f);
+    else b200::fbank_fast_kernel<false, false><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, st>>>(k, f);
   } else {
     k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
     const int64_t grid = (int64_t)B * k.tiles;
@@ -590,7 +598,8 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
-    b200::fbank_fast_kernel<true><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, (cudaStream_t)stream>>>(k, f);
+    if (f.ast_bank) b200::fbank_fast_kernel<true, true><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, (cudaStream_t)stream>>>(k, f);
+    else b200::fbank_fast_kernel<true, false><<<(unsigned)grid, b200::FK_THREADS, p->fast_smem, (cudaStream_t)stream>>>(k, f);
   } else {
     k.tiles = (max_frames + k.tile_frames - 1) / k.tile_frames;
     const int64_t grid = (int64_t)B * k.tiles;
@@ -617,7 +626,7 @@ int b200fbank_resample(const b200fbank_plan* p, const float* d_wav, const int64_
     if (!r.identity) nx = std::max(nx, (chunk / r.nw + 2) * r.orig + r.klen);
   const size_t smem = (size_t)(chunk + align_up(std::max(nx, 4), 4)) * 4;
   if (smem > 227 * 1024) return fail(B200FBANK_ERR_UNSUPPORTED, "resample ratio needs %zu B of shared memory", smem);
-  CUDA_TRY(cudaFuncSetAttribute(b200::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(b200::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   b200::FbankParams k = p->base;
   k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
   k.tiles = (int)((out_clip_samples + chunk - 1) / chunk);

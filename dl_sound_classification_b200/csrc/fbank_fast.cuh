@@ -33,9 +33,14 @@ constexpr int FK_ORIG = 441, FK_NEW = 160, FK_KLEN = 475, FK_WIDTH = 17;
 constexpr int FK_RING_STRIDE = 161;       // hop stride in the ring: odd -> conflict-free column stores
 constexpr int FK_RING_HOPS = 34;
 constexpr int FK_RING_FLOATS = 5476;      // 34 * 161 = 5474, padded to a multiple of 4
-constexpr int FK_EBUF = 1056;             // floats per warp: 512 complex (exchange) / 4 x 264 (power)
-constexpr int FK_PSTRIDE = 264;
+constexpr int FK_EROW = 33;               // float2 per exchange row (32 + 1 pad: conflict-free, no index math)
+constexpr int FK_EBUF = 2 * 16 * FK_EROW * 2;   // floats per warp: two 16 x 33 complex exchange buffers; later 256 x 4 powers
 constexpr int FK_XFLOATS = 15040;         // 33 * 441 + 475 + slack, multiple of 4
+constexpr int FK_TAPFLOATS = FK_NG * FK_GROUP_FLOATS;   // 5632
+// Region AT = [x chunk | taps]; the FFT phase reuses its front as 8 x FK_EBUF exchange buffers, so the
+// taps are re-staged (cp.async, L2-resident) together with every input chunk.
+constexpr int FK_ATFLOATS = FK_XFLOATS + FK_TAPFLOATS;
+static_assert(8 * FK_EBUF <= FK_ATFLOATS, "exchange buffers must fit the x|taps region");
 
 __host__ __device__ constexpr int fk_off(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 7 : 10; }
 
@@ -51,11 +56,12 @@ struct FastParams {
   int mel_rows;           // sum of mel_maxcnt
   int gen_part[B200_MAX_RATES];   // outputs per staging pass for rates on the per-sample path
   int seg_frames, segs;
+  int ast_bank;           // 1: filter lengths per group are (2,3,6,11) -> fully unrolled mel
 };
 
 // Copy x[in_lo, in_lo + nx) of the clip into A[sh + i]; returns sh (0..3), chosen so that
 // 16-B aligned global addresses land on 16-B aligned shared addresses.
-__device__ __forceinline__ int fk_load_x(const ClipInfo& c, int64_t in_lo, int nx, float* A) {
+__device__ __forceinline__ int fk_load_x(const ClipInfo& c, int64_t in_lo, int nx, float* A) {   // [phase: load_x]
   const int tid = threadIdx.x;
   const float* g = c.wav + in_lo;
   const int sh = (int)(((uintptr_t)g >> 2) & 3);
@@ -91,7 +97,7 @@ __device__ __forceinline__ int fk_load_x(const ClipInfo& c, int64_t in_lo, int n
 
 // Per-sample polyphase loop (any rate): resampled samples [s0, s0 + count) -> ring, where
 // ring sample 0 is absolute resampled index ring_base.  xs[i] = x[in_lo + i].
-__device__ __forceinline__ void fk_resample_generic(const RateDev& R, const float* xs, int64_t in_lo,
+__device__ __forceinline__ void fk_resample_generic(const RateDev& R, const float* xs, int64_t in_lo,   // [phase: resample_generic]
                                                     int64_t s0, int count, float* ring, int64_t ring_base) {
   for (int t = threadIdx.x; t < count; t += FK_THREADS) {
     const int64_t s = s0 + t;
@@ -108,7 +114,7 @@ __device__ __forceinline__ void fk_resample_generic(const RateDev& R, const floa
 
 // One resampler task: 5 phases x 32 hops (lane = hop).  T4 = the group's 44 float4 of taps in
 // consumption order, xs = this lane's first input sample, yo = ring slot of phase 5g of this hop.
-__device__ __forceinline__ void fk_resample_group(const float4* __restrict__ T4, const float* __restrict__ xs,
+__device__ __forceinline__ void fk_resample_group(const float4* __restrict__ T4, const float* __restrict__ xs,   // [phase: resample_group]
                                                   float* __restrict__ yo) {
   float acc[FK_RP];
 #pragma unroll
@@ -133,14 +139,201 @@ __device__ __forceinline__ void fk_resample_group(const float4* __restrict__ T4,
   for (int r = 0; r < FK_RP; ++r) yo[r] = acc[r];
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankParams p, const FastParams fp) {
+
+__device__ __forceinline__ void fk_cp_async16(float* dst_smem, const float* src_gmem) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void fk_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Asynchronous variant of fk_load_x for chunks that lie strictly inside the clip (no zero
+// fill): whole 16-B lines, global -> shared without passing through registers.   // [phase: load_x]
+__device__ __forceinline__ int fk_load_x_async(const float* g /* = clip + in_lo */, int nx, float* A) {
+  const int sh = (int)(((uintptr_t)g >> 2) & 3);
+  const float* g0 = g - sh;                       // 16-B aligned
+  const int nvec = (nx + sh + 3) >> 2;
+  for (int v = threadIdx.x; v < nvec; v += FK_THREADS) fk_cp_async16(A + 4 * v, g0 + 4 * v);
+  return sh;
+}
+
+// Per-lane constants of the frame pass (live for the whole kernel).
+struct FkLane {
+  float win[13];        // window at n = lane + 32 j
+  int mstart[4];        // first FFT bin of mel filters lane + 32 i
+  float nmean[4], nscale[4];
+};
+
+// DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.
+// yb = ring + row * 161 + lane.  Loads are unconditional: every ring row holds finite data.   // [phase: stage0_frames]
+__device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, const FkLane& L, float dc_scale,
+                                               float preemph, int lane, float2 (&z)[16]) {
+  const int d0 = lane == 0 ? 0 : 1;        // j = 0: replicate pad at the frame start (kaldi.py:195-198)
+  const int d5 = lane == 0 ? 2 : 1;        // j = 5, 10: n - 1 sits in the previous hop row (stride 161)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float* y = yb + h * FK_RING_STRIDE;
+    float yv[13], s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      yv[j] = y[32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0))];
+      if (j < 12) s += yv[j];
+    }
+    s += lane < 16 ? yv[12] : 0.f;
+    const float mean = warp_sum(s) * dc_scale;
+    const float* y0 = y - d0;
+    const float* y5 = y - d5;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+      const float prev = (j == 0) ? y0[off] : ((j == 5 || j == 10) ? y5[off] : y[off - 1]);
+      const float v = ((yv[j] - mean) - preemph * (prev - mean)) * L.win[j];
+      if (h == 0) z[j].x = v; else z[j].y = v;
+    }
+  }
+#pragma unroll
+  for (int j = 13; j < 16; ++j) z[j] = make_float2(0.f, 0.f);
+}
+
+// 16-point DFT over n1, twiddle W_512^(lane k1), store row k1 of the exchange buffer.   // [phase: fft_stage1]
+__device__ __forceinline__ void fk_stage1_store(float2 (&z)[16], const float2* __restrict__ stw, int lane,
+                                                float2* __restrict__ E) {
+  fft_dif<16>(z);
+  E[lane] = z[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) {
+    const float2 w = stw[k1 * 32 + lane];
+    const float2 a = z[bitrev_n(k1, 4)];
+    E[k1 * FK_EROW + lane] = make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+  }
+}
+
+// Mel filters lane + 32 i over the four frames of P4[k] = (P_f0, P_f1, P_f2, P_f3)[k].   // [phase: mel]
+template <int MC>
+__device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, const float* __restrict__ wrow, int st,
+                                             int mc_dyn, float (&acc)[4]) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  if constexpr (MC >= 0) {
+#pragma unroll
+    for (int j = 0; j < MC; ++j) {
+      const float w = wrow[j * 32];
+      const float4 pv = P4[st + j];
+      acc[0] = fmaf(w, pv.x, acc[0]); acc[1] = fmaf(w, pv.y, acc[1]);
+      acc[2] = fmaf(w, pv.z, acc[2]); acc[3] = fmaf(w, pv.w, acc[3]);
+    }
+  } else {
+    for (int j = 0; j < mc_dyn; ++j) {
+      const float w = wrow[j * 32];
+      const float4 pv = P4[st + j];
+      acc[0] = fmaf(w, pv.x, acc[0]); acc[1] = fmaf(w, pv.y, acc[1]);
+      acc[2] = fmaf(w, pv.z, acc[2]); acc[3] = fmaf(w, pv.w, acc[3]);
+    }
+  }
+}
+
+// One frame pass of a warp: frames f0..f0+3 of the chunk (ring rows f0..f0+5) -> 4 x n_mel outputs.
+// Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths (2,3,6,11) of the AST bank.
+template <bool STATS, bool AST>
+__device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const FkLane& L,
+                                              const float* __restrict__ ring, float* __restrict__ Ebuf,
+                                              const float2* __restrict__ stw, const float* __restrict__ smelw,
+                                              int b, int r0, int f0, int nf, int row_end, int lane,
+                                              int mk0, int mk1, int mk2, int mk3, double (&st_s)[4], double (&st_ss)[4]) {
+  float2* EA = reinterpret_cast<float2*>(Ebuf);
+  float2* EB = EA + 16 * FK_EROW;
+  if (f0 < nf) {
+    const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
+    {
+      float2 z[16];
+      fk_stage0_pair(ring + f0 * FK_RING_STRIDE + lane, L, dc_scale, p.preemph, lane, z);
+      fk_stage1_store(z, stw, lane, EA);
+    }
+    {
+      float2 z[16];
+      fk_stage0_pair(ring + (f0 + 2) * FK_RING_STRIDE + lane, L, dc_scale, p.preemph, lane, z);
+      fk_stage1_store(z, stw, lane, EB);
+    }
+    __syncwarp();
+    // ---- stage 2: lane = k1 + 16 * transform gathers its row, 32-point DFT over n2   // [phase: exchange]
+    const int k1l = lane & 15;
+    float2 u[32];
+    {
+      const float2* row = (lane < 16 ? EA : EB) + k1l * FK_EROW;
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) u[n2] = row[n2];
+    }
+    __syncwarp();
+    fft_dif<32>(u);                                                                    // [phase: fft_stage2]
+    // ---- split the two real spectra (Z[k], conj Z[512-k]) and take |.|^2            // [phase: split_power]
+    const int src = ((16 - k1l) & 15) | (lane & 16);
+    float2* P2 = reinterpret_cast<float2*>(Ebuf) + (lane >> 4) + 2 * k1l;   // P4[k].{xy | zw}, k = k1 + 16 k2
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float2 zk = u[bitrev_n(k2, 5)];
+      const float2 own = u[bitrev_n((32 - k2) & 31, 5)];
+      const float2 oth = u[bitrev_n(31 - k2, 5)];
+      float px = __shfl_sync(0xffffffffu, oth.x, src);
+      float py = __shfl_sync(0xffffffffu, oth.y, src);
+      if (k1l == 0) { px = own.x; py = own.y; }
+      const float ar = zk.x + px, ai = zk.y - py, br = zk.y + py, bi = px - zk.x;
+      float pa = 0.25f * fmaf(ar, ar, ai * ai), pb = 0.25f * fmaf(br, br, bi * bi);
+      if (!p.use_power) { pa = sqrtf(pa); pb = sqrtf(pb); }
+      P2[32 * k2] = make_float2(pa, pb);
+    }
+    __syncwarp();
+  }
+  // ---- mel (lanes = bins), log, normalise, mask, store                              // [phase: mel]
+  const float4* P4 = reinterpret_cast<const float4*>(Ebuf);
+  const float tmean = p.n_stats > 0 ? p.target_mean : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= fp.mel_groups) continue;
+    const int m = lane + 32 * i;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (f0 < nf) {
+      const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
+      if (AST) {
+        if (i == 0) fk_mel_group<2>(P4, wrow, L.mstart[i], 0, acc);
+        else if (i == 1) fk_mel_group<3>(P4, wrow, L.mstart[i], 0, acc);
+        else if (i == 2) fk_mel_group<6>(P4, wrow, L.mstart[i], 0, acc);
+        else fk_mel_group<11>(P4, wrow, L.mstart[i], 0, acc);
+      } else {
+        fk_mel_group<-1>(P4, wrow, L.mstart[i], fp.mel_maxcnt[i], acc);
+      }
+    }
+    if (m < p.n_mel) {                                                                 // [phase: epilogue_store]
+      float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + (r0 + f0)) * p.n_cols + m
+                               : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + (r0 + f0);
+      const int ostep = p.layout == 0 ? p.n_cols : 1;
+      const bool fmask = (m >= mk2 && m < mk2 + mk3);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int t = r0 + f0 + h;
+        const bool live = (f0 + h) < nf;
+        float x = acc[h];
+        if (p.use_log) x = x > B200_FLT_EPSILON ? __logf(x) : B200_LOG_FLT_EPSILON;   // exact floor value (kaldi.py:633)
+        if (STATS) {
+          if (live) { st_s[i] += (double)x; st_ss[i] += (double)x * (double)x; }
+        } else if (t < row_end) {
+          x = live ? x : 0.f;
+          x = fmaf(x - L.nmean[i], L.nscale[i], tmean);
+          if (fmask || (t >= mk0 && t < mk0 + mk1)) x = 0.f;
+          o[h * ostep] = x;
+        }
+      }
+    }
+  }
+}
+
+template <bool STATS, bool AST>
+__global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankParams p, const FastParams fp) {   // [phase: setup]
   extern __shared__ __align__(16) float smem[];
-  float* A = smem;                                   // [FK_XFLOATS] input chunk, later per-warp exchange / power
-  float* ring = A + FK_XFLOATS;                      // [FK_RING_FLOATS] 16 kHz samples, 34 hops x 161
-  float* staps = ring + FK_RING_FLOATS;              // [32 * 176]
-  float2* stw = reinterpret_cast<float2*>(staps + FK_NG * FK_GROUP_FLOATS);   // [512]
-  float* smelw = reinterpret_cast<float*>(stw + 512);                         // [mel_rows * 32]
+  float* A = smem;                                   // [FK_XFLOATS] input chunk | [FK_TAPFLOATS] taps; FFT phase: exchange
+  float* staps = A + FK_XFLOATS;
+  float* ring = A + FK_ATFLOATS;                     // [FK_RING_FLOATS] 16 kHz samples, 34 hops x 161
+  float2* stw = reinterpret_cast<float2*>(ring + FK_RING_FLOATS);   // [512]
+  float* smelw = reinterpret_cast<float*>(stw + 512);               // [mel_rows * 32]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / fp.segs;
@@ -157,30 +350,23 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
   const int rid = p.rate_id ? p.rate_id[b] : 0;
   const bool fast = (rid == fp.fast_rate_id);
 
-  // ---- one-time staging of the tables -------------------------------------------------------
+  // ---- one-time staging of the small tables ---------------------------------------------------
   if (row_begin < m_eff) {
-    if (fast) {
-      const float4* src = reinterpret_cast<const float4*>(fp.taps);
-      float4* dst = reinterpret_cast<float4*>(staps);
-      for (int i = tid; i < FK_NG * FK_GROUP_FLOATS / 4; i += FK_THREADS) dst[i] = __ldg(src + i);
-    }
     for (int i = tid; i < 512; i += FK_THREADS) stw[i] = __ldg(fp.tw + i);
     for (int i = tid; i < fp.mel_rows * 32; i += FK_THREADS) smelw[i] = __ldg(fp.melw + i);
   }
-  float win[13];
+  FkLane L;
 #pragma unroll
-  for (int j = 0; j < 13; ++j) win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
-  int mstart[4];
-  float nmean[4], nscale[4];
+  for (int j = 0; j < 13; ++j) L.win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = lane + 32 * i;
-    mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
-    nmean[i] = 0.f; nscale[i] = 1.f;
+    L.mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
+    L.nmean[i] = 0.f; L.nscale[i] = 1.f;
     if (!STATS && p.n_stats > 0 && m < p.n_mel) {
       const int si = p.n_stats == 1 ? 0 : m;
-      nmean[i] = __ldg(p.mean + si);
-      nscale[i] = p.target_std / __ldg(p.std + si);
+      L.nmean[i] = __ldg(p.mean + si);
+      L.nscale[i] = p.target_std / __ldg(p.std + si);
     }
   }
   int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
@@ -188,30 +374,36 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
     mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
     mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
   }
-  const float dc_on = p.remove_dc ? 1.f : 0.f;
   double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
   __syncthreads();
 
   bool ring_valid = false;
-  for (int r0 = row_begin; r0 < row_end; r0 += FK_CH) {
+  for (int r0 = row_begin; r0 < row_end; r0 += FK_CH) {   // [phase: chunk_control]
     int nf = m_eff - r0;
     nf = nf < 0 ? 0 : (nf > FK_CH ? FK_CH : nf);
     if (nf > 0) {
       // ================= resample: fill ring hops [hop_lo, 34) =============================
       const int hop_lo = ring_valid ? 2 : 0;
-      if (ring_valid) {          // carry the last two hops to the front
-        float keep0 = 0.f, keep1 = 0.f;
-        if (tid < 2 * FK_RING_STRIDE) keep0 = ring[32 * FK_RING_STRIDE + tid];
-        if (tid + FK_THREADS < 2 * FK_RING_STRIDE) keep1 = ring[32 * FK_RING_STRIDE + tid + FK_THREADS];
-        __syncthreads();
-        if (tid < 2 * FK_RING_STRIDE) ring[tid] = keep0;
-        if (tid + FK_THREADS < 2 * FK_RING_STRIDE) ring[tid + FK_THREADS] = keep1;
-      }
       const int64_t ring_base = (int64_t)r0 * FK_SHIFT;          // absolute index of ring sample 0
       if (fast) {
         const int64_t in_lo = (int64_t)(r0 + hop_lo) * FK_ORIG - FK_WIDTH;
         const int nx = (FK_RING_HOPS - hop_lo - 1) * FK_ORIG + FK_KLEN + 8;
-        const int sh = fk_load_x(c, in_lo, nx, A);
+        const float* g = c.wav + in_lo;
+        // taps ride along with the chunk (they were overwritten by the exchange buffers)
+        for (int v = tid; v < FK_TAPFLOATS / 4; v += FK_THREADS) fk_cp_async16(staps + 4 * v, fp.taps + 4 * v);
+        int sh;
+        const bool interior = in_lo >= 4 && in_lo + nx + 4 <= c.n_in && (g - 4 >= p.wav);
+        if (interior) sh = fk_load_x_async(g, nx, A);
+        else sh = fk_load_x(c, in_lo, nx, A);
+        if (ring_valid) {          // carry the last two hops to the front while the copies fly
+          float keep0 = 0.f, keep1 = 0.f;
+          if (tid < 2 * FK_RING_STRIDE) keep0 = ring[32 * FK_RING_STRIDE + tid];
+          if (tid + FK_THREADS < 2 * FK_RING_STRIDE) keep1 = ring[32 * FK_RING_STRIDE + tid + FK_THREADS];
+          __syncthreads();
+          if (tid < 2 * FK_RING_STRIDE) ring[tid] = keep0;
+          if (tid + FK_THREADS < 2 * FK_RING_STRIDE) ring[tid + FK_THREADS] = keep1;
+        }
+        fk_cp_async_wait_all();
         __syncthreads();
         const float* xs = A + sh;
         if (!ring_valid)       // prologue: hops 0 and 1 on the per-sample path
@@ -220,31 +412,41 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
         float* yl = ring + (2 + lane) * FK_RING_STRIDE;
 #pragma unroll 1
         for (int gi = 0; gi < FK_NG / 8; ++gi) {
-          const int g = warp * (FK_NG / 8) + gi;
-          fk_resample_group(reinterpret_cast<const float4*>(staps + g * FK_GROUP_FLOATS),
-                            xl + __ldg(fp.k0g + g), yl + FK_RP * g);
-        }
-      } else if (c.R.identity) {
-        const int cnt = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
-        const int64_t s0 = ring_base + hop_lo * FK_SHIFT;
-        for (int t = tid; t < cnt; t += FK_THREADS) {
-          const int64_t s = s0 + t;
-          const int rel = (int)(s - ring_base);
-          ring[rel + rel / FK_SHIFT] = (s < c.n_in) ? __ldg(c.wav + s) : 0.f;
+          const int g2 = warp * (FK_NG / 8) + gi;
+          fk_resample_group(reinterpret_cast<const float4*>(staps + g2 * FK_GROUP_FLOATS),
+                            xl + __ldg(fp.k0g + g2), yl + FK_RP * g2);
         }
       } else {
-        const int total = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
-        const int part = fp.gen_part[rid];
-        for (int done = 0; done < total; done += part) {
-          const int cnt = (total - done < part) ? total - done : part;
-          const int64_t s0 = ring_base + hop_lo * FK_SHIFT + done;
-          const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
-          const int64_t in_lo = q_lo * c.R.orig - c.R.width;
-          const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
-          if (done > 0) __syncthreads();
-          const int sh = fk_load_x(c, in_lo, nx, A);
+        if (ring_valid) {
+          float keep0 = 0.f, keep1 = 0.f;
+          if (tid < 2 * FK_RING_STRIDE) keep0 = ring[32 * FK_RING_STRIDE + tid];
+          if (tid + FK_THREADS < 2 * FK_RING_STRIDE) keep1 = ring[32 * FK_RING_STRIDE + tid + FK_THREADS];
           __syncthreads();
-          fk_resample_generic(c.R, A + sh, in_lo, s0, cnt, ring, ring_base);
+          if (tid < 2 * FK_RING_STRIDE) ring[tid] = keep0;
+          if (tid + FK_THREADS < 2 * FK_RING_STRIDE) ring[tid + FK_THREADS] = keep1;
+        }
+        if (c.R.identity) {
+          const int cnt = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
+          const int64_t s0 = ring_base + hop_lo * FK_SHIFT;
+          for (int t = tid; t < cnt; t += FK_THREADS) {
+            const int64_t s = s0 + t;
+            const int rel = (int)(s - ring_base);
+            ring[rel + rel / FK_SHIFT] = (s < c.n_in) ? __ldg(c.wav + s) : 0.f;
+          }
+        } else {
+          const int total = (FK_RING_HOPS - hop_lo) * FK_SHIFT;
+          const int part = fp.gen_part[rid];
+          for (int done = 0; done < total; done += part) {
+            const int cnt = (total - done < part) ? total - done : part;
+            const int64_t s0 = ring_base + hop_lo * FK_SHIFT + done;
+            const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
+            const int64_t in_lo = q_lo * c.R.orig - c.R.width;
+            const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
+            if (done > 0) __syncthreads();
+            const int sh = fk_load_x(c, in_lo, nx, A);
+            __syncthreads();
+            fk_resample_generic(c.R, A + sh, in_lo, s0, cnt, ring, ring_base);
+          }
         }
       }
       __syncthreads();
@@ -252,137 +454,9 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
     }
 
     // ================= FFT + mel: warp w owns frames 4w .. 4w+3 of the chunk ===============
-    const int f0 = 4 * warp;
-    float* Pw = A + warp * FK_EBUF;
-    const bool any_live = f0 < nf;
-    if (any_live) {
-      float2 z1[16], z2[16];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const bool live = (f0 + h) < nf;
-        const float* yb = ring + (f0 + h) * FK_RING_STRIDE + lane;
-        float yv[13], s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
-          const bool ok = live && (j < 12 || lane < 16);
-          yv[j] = ok ? yb[off] : 0.f;
-          s += yv[j];
-        }
-        const float mean = warp_sum(s) * (dc_on / (float)FK_SIZE);
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
-          const bool ok = live && (j < 12 || lane < 16);
-          float prev;
-          if (j == 0) {
-            const float pv = ok ? yb[lane == 0 ? off : off - 1] : 0.f;   // replicate pad at the frame start
-            prev = pv;
-          } else if (j == 5 || j == 10) {
-            prev = ok ? yb[lane == 0 ? off - 2 : off - 1] : 0.f;          // previous sample sits in the previous hop row
-          } else {
-            prev = ok ? yb[off - 1] : 0.f;
-          }
-          const float v = ((yv[j] - mean) - p.preemph * (prev - mean)) * win[j];
-          if (h == 0) z1[j].x = v; else if (h == 1) z1[j].y = v; else if (h == 2) z2[j].x = v; else z2[j].y = v;
-        }
-      }
-#pragma unroll
-      for (int j = 13; j < 16; ++j) { z1[j] = make_float2(0.f, 0.f); z2[j] = make_float2(0.f, 0.f); }
-
-      // ---- stage 1: 16-point DFT over n1 (n = lane + 32 n1), twiddle W_512^(lane * k1) ----
-      fft_dif<16>(z1);
-      fft_dif<16>(z2);
-#pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) {
-        const float2 w = stw[k1 * 32 + lane];
-        constexpr int dummy = 0; (void)dummy;
-        const int slot = bitrev_n(k1, 4);
-        const float2 a = z1[slot], bq = z2[slot];
-        z1[slot] = make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
-        z2[slot] = make_float2(fmaf(-bq.y, w.y, bq.x * w.x), fmaf(bq.y, w.x, bq.x * w.y));
-      }
-
-      // ---- exchange through smem (XOR swizzle), one transform at a time ---------------------
-      float2* E = reinterpret_cast<float2*>(Pw);
-      float2 u[32];
-      const int k1l = lane & 15;
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) E[k1 * 32 + (lane ^ k1)] = z1[bitrev_n(k1, 4)];
-      __syncwarp();
-      if (lane < 16) {
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) u[n2] = E[k1l * 32 + (n2 ^ k1l)];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) E[k1 * 32 + (lane ^ k1)] = z2[bitrev_n(k1, 4)];
-      __syncwarp();
-      if (lane >= 16) {
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) u[n2] = E[k1l * 32 + (n2 ^ k1l)];
-      }
-      __syncwarp();
-
-      // ---- stage 2: 32-point DFT over n2; lane = k1 + 16 * transform ------------------------
-      fft_dif<32>(u);
-
-      // ---- split the two real spectra (Z[k], conj Z[512-k]) and take |.|^2 ------------------
-      const int src = ((16 - k1l) & 15) | (lane & 16);
-      const int prow = (lane >> 4) * 2 * FK_PSTRIDE + k1l;
-#pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const float2 zk = u[bitrev_n(k2, 5)];
-        const float2 own = u[bitrev_n((32 - k2) & 31, 5)];
-        const float2 oth = u[bitrev_n(31 - k2, 5)];
-        float px = __shfl_sync(0xffffffffu, oth.x, src);
-        float py = __shfl_sync(0xffffffffu, oth.y, src);
-        if (k1l == 0) { px = own.x; py = own.y; }
-        const float ar = zk.x + px, ai = zk.y - py, br = zk.y + py, bi = px - zk.x;
-        float pa = 0.25f * fmaf(ar, ar, ai * ai), pb = 0.25f * fmaf(br, br, bi * bi);
-        if (!p.use_power) { pa = sqrtf(pa); pb = sqrtf(pb); }
-        Pw[prow + 16 * k2] = pa;
-        Pw[prow + FK_PSTRIDE + 16 * k2] = pb;
-      }
-      __syncwarp();
-    }
-
-    // ---- mel (lanes = bins), log, epilogue, store ---------------------------------------------
-    for (int i = 0; i < fp.mel_groups; ++i) {
-      const int m = lane + 32 * i;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (any_live) {
-        const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
-        const int st = mstart[i];
-        const int mc = fp.mel_maxcnt[i];
-        for (int j = 0; j < mc; ++j) {
-          const float w = wrow[j * 32];
-          int kk = st + j;
-          kk = kk > 255 ? 255 : kk;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) acc[h] = fmaf(w, Pw[h * FK_PSTRIDE + kk], acc[h]);
-        }
-      }
-      if (m < p.n_mel) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int t = r0 + f0 + h;
-          const bool live = (f0 + h) < nf;
-          float x = acc[h];
-          if (p.use_log) x = x > B200_FLT_EPSILON ? __logf(x) : B200_LOG_FLT_EPSILON;   // exact floor value (kaldi.py:633)
-          if (STATS) {
-            if (live) { st_s[i] += (double)x; st_ss[i] += (double)x * (double)x; }
-          } else if (t < row_end) {
-            x = live ? x : 0.f;
-            x = fmaf(x - nmean[i], nscale[i], p.n_stats > 0 ? p.target_mean : 0.f);
-            if ((t >= mk0 && t < mk0 + mk1) || (m >= mk2 && m < mk2 + mk3)) x = 0.f;
-            if (p.layout == 0) p.out[((size_t)b * p.out_frames + t) * p.n_cols + m] = x;
-            else p.out[((size_t)b * p.n_cols + m) * p.out_frames + t] = x;
-          }
-        }
-      }
-    }
-    __syncthreads();      // A (exchange / power) and the ring are reused by the next chunk
+    fk_frame_pass<STATS, AST>(p, fp, L, ring, A + warp * FK_EBUF, stw, smelw, b, r0, 4 * warp, nf, row_end, lane,
+                              mk0, mk1, mk2, mk3, st_s, st_ss);
+    __syncthreads();      // the x|taps region (exchange / power) and the ring are reused by the next chunk   // [phase: chunk_control]
   }
 
   if (STATS) {
