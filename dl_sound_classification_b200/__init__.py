@@ -8,6 +8,12 @@ raises if the library has not been built -- there is no CPU fallback.
 from . import _capi
 from .frontend import AST_FBANK_KWARGS, FbankFrontend, launch_count
 from .kaldi import fbank
+from .preprocessing import (ASTPreprocessor, B200ASTPreprocessor, BasePreprocessor, PreprocessingConfig,
+                            create_preprocessor, resample_waveform)
+from .specaugment import SpecAugment
+from .stats import DatasetStats, NormStats, finalize_sums
 
-__all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi"]
+__all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi", "ASTPreprocessor",
+           "B200ASTPreprocessor", "BasePreprocessor", "PreprocessingConfig", "create_preprocessor",
+           "resample_waveform", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums"]
 __version__ = "0.1.0"

@@ -80,16 +80,19 @@ def _load():
     lib.b200fbank_resample.restype = C.c_int
     lib.b200fbank_launch_count.argtypes = [C.c_int]
     lib.b200fbank_launch_count.restype = I64
+    lib.b200fbank_sizeof_opts.restype = C.c_int
     v = lib.b200fbank_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"libb200fbank ABI {v} != expected {ABI_VERSION}; rebuild")
+    if lib.b200fbank_sizeof_opts() != C.sizeof(Opts):
+        raise ImportError("b200fbank_opts layout mismatch between include/b200fbank.h and _capi.Opts; rebuild")
     return lib
 
 
 lib = _load()
 
 EXPORTED_SYMBOLS = [
-    "b200fbank_abi_version", "b200fbank_default_opts", "b200fbank_plan_create", "b200fbank_plan_destroy",
+    "b200fbank_abi_version", "b200fbank_sizeof_opts", "b200fbank_default_opts", "b200fbank_plan_create", "b200fbank_plan_destroy",
     "b200fbank_last_error", "b200fbank_resampled_length", "b200fbank_num_frames", "b200fbank_num_cols",
     "b200fbank_plan_table", "b200fbank_plan_info", "b200fbank_execute", "b200fbank_stats_accumulate",
     "b200fbank_resample", "b200fbank_launch_count",

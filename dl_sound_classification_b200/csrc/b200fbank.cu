@@ -458,6 +458,7 @@ int check_device_call(const b200fbank_plan* p, const void* wav, const int64_t* o
 extern "C" {
 
 int b200fbank_abi_version(void) { return B200FBANK_ABI_VERSION; }
+int b200fbank_sizeof_opts(void) { return (int)sizeof(b200fbank_opts); }
 
 void b200fbank_default_opts(b200fbank_opts* o) {
   memset(o, 0, sizeof *o);

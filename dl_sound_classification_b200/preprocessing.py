@@ -1,0 +1,322 @@
+"""Drop-in mirror of the reference's AST preprocessing interface (src/datasets/preprocessing.py).
+
+Same names, arguments and error behaviour as ``PreprocessingConfig`` (:612-680),
+``BasePreprocessor`` (:683-792), ``ASTPreprocessor`` (:971-1113), ``resample_waveform``
+(:61-76) and ``create_preprocessor`` (:1315-1346) -- computed by the fused sm_100a kernel.
+
+New OPTIONAL config keys (free-form kwargs already flow through the reference's Hydra
+configs untouched): ``frontend`` ("kaldi_fbank", the north_star recipe),
+``target_sample_rate`` (16000), ``target_frames`` (None = the clip's own frame count),
+``window_type`` ("hanning"), ``norm_mean`` / ``norm_std`` (dataset statistics, scalar or
+per-bin; None + ``normalize`` = the reference's per-clip mean / unbiased std), ``extra_rates``.
+Out of scope: the gzip/pickle disk cache -- GPU recompute
+makes it moot, ``preprocess_with_cache`` simply recomputes -- and the EnvNet/CNN modes.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import logging
+import random
+from abc import ABC, abstractmethod
+from functools import lru_cache
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from . import specaugment as _sa
+from .frontend import AST_FBANK_KWARGS, FbankFrontend, _require_cuda
+
+logger = logging.getLogger(__name__)
+
+AST_HOP_LENGTH = 160      # src/datasets/preprocessing.py:55-58
+AST_N_FFT = 1024
+AST_WIN_LENGTH = 400
+
+
+class PreprocessingConfig:
+    """Free-form kwargs bag + md5 hash (src/datasets/preprocessing.py:612-680)."""
+
+    def __init__(self, **kwargs):
+        self.config = kwargs
+        self._hash = None
+        self._validation_errors: List[str] = []
+
+    def get_hash(self) -> str:
+        if self._hash is None:
+            import platform
+            system_info = {"python_version": platform.python_version(), "torch_version": torch.__version__,
+                           "platform": platform.platform()}
+
+            def plain(obj):
+                if hasattr(obj, "_content") and hasattr(obj, "items"):
+                    return {k: plain(v) for k, v in obj.items()}
+                if isinstance(obj, (list, tuple)):
+                    return [plain(v) for v in obj]
+                if isinstance(obj, torch.Tensor):
+                    return obj.tolist()
+                return obj
+            s = json.dumps({"config": plain(self.config), "system_info": system_info}, sort_keys=True, default=str)
+            self._hash = hashlib.md5(s.encode()).hexdigest()[:12]
+        return self._hash
+
+    def validate(self) -> bool:
+        self._validation_errors = []
+        c = self.config
+        if "sample_rate" in c and (not isinstance(c["sample_rate"], int) or c["sample_rate"] <= 0):
+            self._validation_errors.append("sample_rate must be a positive integer")
+        if "n_mels" in c and (not isinstance(c["n_mels"], int) or c["n_mels"] <= 0):
+            self._validation_errors.append("n_mels must be a positive integer")
+        if "window_length" in c and (not isinstance(c["window_length"], (int, float)) or c["window_length"] <= 0):
+            self._validation_errors.append("window_length must be a positive number")
+        return len(self._validation_errors) == 0
+
+    def get_validation_errors(self) -> List[str]:
+        return self._validation_errors.copy()
+
+    def __getattr__(self, name: str) -> Any:
+        cfg = self.__dict__.get("config", {})
+        if name in cfg:
+            return cfg[name]
+        raise AttributeError(f"'{self.__class__.__name__}' object has no attribute '{name}'")
+
+
+class BasePreprocessor(ABC):
+    """src/datasets/preprocessing.py:683-792 without the disk cache (out of scope)."""
+
+    def __init__(self, config: PreprocessingConfig):
+        self.config = config
+        self.cache_manager = None
+        self._performance_stats: List[float] = []
+
+    @abstractmethod
+    def preprocess(self, waveform: torch.Tensor, sample_rate: int) -> torch.Tensor:
+        ...
+
+    @abstractmethod
+    def get_cache_suffix(self) -> str:
+        ...
+
+    def multi_crop_test(self, waveform: torch.Tensor) -> List[torch.Tensor]:
+        return [self.preprocess(waveform, self.config.config.get("sample_rate", 44100))]
+
+    def setup_cache(self, base_cache_dir: Path, force_rebuild: bool = False, max_cache_size_gb: float = 5.0) -> None:
+        """Accepted for signature compatibility; features are recomputed on the GPU, never cached."""
+        self.cache_manager = None
+
+    def preprocess_with_cache(self, waveform: torch.Tensor, sample_rate: int,
+                              original_path: Optional[Path] = None) -> torch.Tensor:
+        return self.preprocess(waveform, sample_rate)
+
+    def get_cache_stats(self):
+        return None
+
+    def cleanup_cache(self, max_age_days: int = 30) -> None:
+        return None
+
+    def get_performance_stats(self) -> Dict[str, float]:
+        return {}
+
+
+@lru_cache(maxsize=16)
+def _resampler(device_index: int, orig: int, new: int) -> FbankFrontend:
+    # only the rate table matters for b200fbank_resample; the fbank options are placeholders
+    return FbankFrontend(orig_rates=(orig,), device=torch.device("cuda", device_index), sample_frequency=float(new),
+                         num_mel_bins=23, high_freq=0.0, low_freq=0.0 if new < 100 else 20.0)
+
+
+def resample_waveform(waveform: torch.Tensor, current_rate: int, target_rate: int) -> torch.Tensor:
+    """src/datasets/preprocessing.py:61-76: ``Resample(current, target)(waveform)`` or the input itself
+    when the rates match.  ``waveform`` is ``(..., time)``; the result lives on the input's device."""
+    if current_rate == target_rate:
+        return waveform
+    if not waveform.is_floating_point():
+        raise TypeError(f"Expected floating point type for waveform tensor, but received {waveform.dtype}.")
+    if int(current_rate) != current_rate or int(target_rate) != target_rate:
+        raise Exception("Frequencies must be of integer type to ensure quality resampling computation.")
+    dev = _require_cuda(waveform.device if waveform.is_cuda else None)
+    fe = _resampler(dev.index, int(current_rate), int(target_rate))
+    shape = waveform.shape
+    flat = waveform.reshape(-1, shape[-1]).to(device=dev, dtype=torch.float32)
+    out = fe.resample(flat).reshape(shape[:-1] + (-1,))
+    return out.to(device=waveform.device, dtype=waveform.dtype)
+
+
+class ASTPreprocessor(BasePreprocessor):
+    """B200 drop-in for ``ASTPreprocessor`` (src/datasets/preprocessing.py:971-1113).
+
+    ``preprocess(waveform[1, N], sample_rate) -> [1, n_mels, T]`` float32 on the input's device
+    (the reference's per-clip contract); ``preprocess_batch`` is the batched GPU entry point a
+    DataModule hook (``on_after_batch_transfer``) should call.
+    """
+
+    def __init__(self, config: PreprocessingConfig, device=None):
+        super().__init__(config)
+        c = config.config
+        self.n_mels = c.get("n_mels", 128)
+        self.sample_rate = c.get("sample_rate", 44100)
+        self.target_mean = c.get("target_mean", 0.0)
+        self.target_std = c.get("target_std", 0.5)
+        self.normalize = c.get("normalize", True)
+        self.frontend_name = c.get("frontend", "kaldi_fbank")
+        self.target_sample_rate = int(c.get("target_sample_rate", 16000))
+        self.target_frames = c.get("target_frames", None)
+        self.window_type = c.get("window_type", "hanning")
+        self.norm_mean = c.get("norm_mean", None)
+        self.norm_std = c.get("norm_std", None)
+        if (self.norm_mean is None) != (self.norm_std is None):
+            raise ValueError("norm_mean and norm_std must be given together")
+        if self.frontend_name not in ("kaldi_fbank", "melspectrogram"):
+            raise ValueError(f"Unknown frontend: {self.frontend_name}")
+        if self.frontend_name == "melspectrogram":
+            raise NotImplementedError("frontend='melspectrogram' (the reference's MelSpectrogram+AmplitudeToDB recipe, "
+                                      "SURVEY.md section 8f N1) is not built yet; use frontend='kaldi_fbank'")
+        self.n_fft, self.hop_length, self.win_length = AST_N_FFT, AST_HOP_LENGTH, AST_WIN_LENGTH
+        rates = [int(self.sample_rate)] + [int(r) for r in c.get("extra_rates", ())]
+        self.rates = tuple(dict.fromkeys(rates))
+        kw = dict(AST_FBANK_KWARGS, num_mel_bins=int(self.n_mels), sample_frequency=float(self.target_sample_rate),
+                  window_type=self.window_type)
+        self._device = device
+        self._kw = kw
+        self._fe: Optional[FbankFrontend] = None
+        self.mixup = None
+
+    # the plan is created lazily so that constructing the object needs no GPU (config plumbing, hashing)
+    @property
+    def frontend(self) -> FbankFrontend:
+        if self._fe is None:
+            self._fe = FbankFrontend(orig_rates=self.rates, device=_require_cuda(self._device), **self._kw)
+        return self._fe
+
+    def get_cache_suffix(self) -> str:
+        return f"ast_{self.config.get_hash()}"
+
+    # ------------------------------------------------------------------------------------------
+    def preprocess_batch(self, waveforms: torch.Tensor, sample_rate, lengths: Optional[Sequence[int]] = None,
+                         masks: Optional[torch.Tensor] = None, target_frames: Optional[int] = None):
+        """``(B, N)`` (or flat ragged + ``lengths``) -> ``((B, 1, n_mels, T), n_frames[B])`` on the GPU.
+        ``sample_rate`` is an int or a per-clip sequence drawn from the plan's rate table."""
+        fe = self.frontend
+        if isinstance(sample_rate, int):
+            rid_list = None if fe.rate_id(sample_rate) == 0 and len(fe.orig_rates) == 1 else None
+            rate_ids = None
+            rid0 = fe.rate_id(sample_rate)
+            B = waveforms.shape[0] if lengths is None else len(lengths)
+            if rid0 != 0:
+                rate_ids = torch.full((B,), rid0, dtype=torch.int32)
+            del rid_list
+        else:
+            rate_ids = torch.tensor([fe.rate_id(int(r)) for r in sample_rate], dtype=torch.int32)
+        offsets = None
+        if lengths is not None:
+            lens = torch.as_tensor(list(lengths), dtype=torch.int64)
+            offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+            max_len = [int(x) for x in lens]
+        else:
+            max_len = [int(waveforms.shape[-1])] * int(waveforms.shape[0])
+        T = target_frames if target_frames is not None else self.target_frames
+        if T is None:
+            rids = [0] * len(max_len) if rate_ids is None else rate_ids.tolist()
+            T = max(fe.num_frames(n, r) for n, r in zip(max_len, rids))
+            if T <= 0:
+                raise AssertionError("choose a window size {} that is [2, {}]".format(fe.plan.window_size, min(max_len)))
+        mean = std = None
+        if self.normalize and self.norm_mean is not None:
+            mean, std = self.norm_mean, self.norm_std
+        per_clip = self.normalize and self.norm_mean is None
+        out, nfr = fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids,
+                      masks=None if per_clip else masks, mean=mean, std=std, target_mean=self.target_mean,
+                      target_std=self.target_std, layout="bft")
+        if per_clip:
+            out = self._per_clip_normalize(out, nfr)
+            if masks is not None:
+                m = masks.to(out.device)
+                for i in range(out.shape[0]):
+                    out[i] = _sa.apply_intervals(out[i], m[i].tolist())
+        return out, nfr
+
+    def _per_clip_normalize(self, x: torch.Tensor, nfr: torch.Tensor) -> torch.Tensor:
+        """The reference's per-clip statistics (src/datasets/preprocessing.py:1030-1037): global mean and
+        UNBIASED std over the clip's own frames, skipped when std == 0."""
+        out = x.clone()
+        for i in range(x.shape[0]):
+            m = int(nfr[i])
+            v = x[i, :, :, :m]
+            if v.numel() < 2:
+                continue
+            mu, sd = v.mean(), v.std()
+            if float(sd) > 0:
+                out[i, :, :, :m] = (v - mu) / sd * self.target_std + self.target_mean
+        return out
+
+    def preprocess(self, waveform: torch.Tensor, sample_rate: int) -> torch.Tensor:
+        if waveform.dim() == 1:
+            waveform = waveform.unsqueeze(0)
+        in_device = waveform.device
+        out, _ = self.preprocess_batch(waveform[:1].to(torch.float32), int(sample_rate))
+        out = out[0]                                            # (1, n_mels, T)
+        return out if out.device == in_device else out.to(in_device)
+
+    def multi_crop_test(self, waveform: torch.Tensor) -> List[torch.Tensor]:
+        """src/datasets/preprocessing.py:1041-1073: ten evenly spaced 5 s crops (one batched launch here)."""
+        total_length = waveform.shape[-1]
+        n_crops = 10
+        if total_length <= self.sample_rate * 5:
+            return [self.preprocess(waveform, self.sample_rate)]
+        crop_length = int(self.sample_rate * 5)
+        starts = torch.linspace(0, total_length - crop_length, n_crops).long()
+        crops = torch.stack([waveform[..., int(s):int(s) + crop_length].reshape(-1) for s in starts])
+        out, _ = self.preprocess_batch(crops.to(torch.float32), int(self.sample_rate))
+        out = out.to(waveform.device)
+        return [out[i] for i in range(n_crops)]
+
+    def apply_specaugment(self, spectrogram: torch.Tensor, time_mask: int = 192, freq_mask: int = 48) -> torch.Tensor:
+        """src/datasets/preprocessing.py:1075-1104: clones, draws four ``random.randint`` (time first), zero-fills."""
+        channels, n_mels, n_frames = spectrogram.shape
+        return _sa.apply_intervals(spectrogram, _sa.reference_intervals(n_frames, n_mels, time_mask, freq_mask, random))
+
+    def draw_specaugment_masks(self, batch: int, n_frames, time_mask: int = 192, freq_mask: int = 48) -> torch.Tensor:
+        """Mask table for the fused path; same RNG consumption as ``batch`` sequential ``apply_specaugment`` calls."""
+        return _sa.draw_masks(batch, n_frames, int(self.n_mels), time_mask, freq_mask, "reference", random)
+
+    def apply_mixup(self, spec1, spec2, label1, label2, num_classes):
+        raise NotImplementedError("mixup is the step after the frontend (SURVEY.md section 8f N3), not built yet")
+
+
+B200ASTPreprocessor = ASTPreprocessor
+
+
+class PreprocessingCache:
+    """src/datasets/preprocessing.py:1116-1174 reduced to the dispatch it performs for mode 'ast'."""
+
+    def __init__(self, base_cache_dir: Path, max_cache_size_gb: float = 5.0):
+        self.base_cache_dir = Path(base_cache_dir)
+        self.max_cache_size_gb = max_cache_size_gb
+        self.preprocessors: Dict[str, BasePreprocessor] = {}
+
+    def get_preprocessor(self, mode: str, config: PreprocessingConfig) -> BasePreprocessor:
+        if not config.validate():
+            raise ValueError(f"Invalid preprocessing config: {config.get_validation_errors()}")
+        if mode == "ast":
+            return ASTPreprocessor(config)
+        if mode in ("envnet_v2", "cnn_esc50"):
+            raise NotImplementedError(f"preprocessing mode {mode!r} is outside the B200 frontend's scope (AST path only)")
+        raise ValueError(f"Unknown preprocessing mode: {mode}")
+
+    def setup_preprocessor(self, mode: str, config: PreprocessingConfig, force_rebuild: bool = False) -> BasePreprocessor:
+        key = f"{mode}_{config.get_hash()}"
+        if key in self.preprocessors and not force_rebuild:
+            return self.preprocessors[key]
+        pre = self.get_preprocessor(mode, config)
+        pre.setup_cache(self.base_cache_dir, force_rebuild=force_rebuild, max_cache_size_gb=self.max_cache_size_gb)
+        self.preprocessors[key] = pre
+        return pre
+
+
+def create_preprocessor(mode: str, config_dict: Dict[str, Any], base_cache_dir: Path, force_rebuild: bool = False,
+                        max_cache_size_gb: float = 5.0) -> BasePreprocessor:
+    """src/datasets/preprocessing.py:1315-1346.  Never falls back: errors propagate (the reference's caller
+    swallows them into a "basic mode", src/datasets/esc50.py:149-160 -- a GPU drop-in must not)."""
+    config = PreprocessingConfig(**config_dict)
+    return PreprocessingCache(base_cache_dir, max_cache_size_gb).setup_preprocessor(mode, config, force_rebuild)

@@ -102,6 +102,8 @@ typedef struct {
 typedef struct b200fbank_plan b200fbank_plan;
 
 int b200fbank_abi_version(void);
+/* sizeof(b200fbank_opts) as compiled into the library (binding sanity check). */
+int b200fbank_sizeof_opts(void);
 
 /* Fill `o` with the defaults of kaldi.fbank (torchaudio/compliance/kaldi.py:514-541) and
    Resample (torchaudio/transforms/_transforms.py:945-953); n_rates = 1, orig_rates[0] = 16000. */

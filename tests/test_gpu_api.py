@@ -1,0 +1,217 @@
+"""GPU tests of the reference-facing API (ASTPreprocessor mirror, resample_waveform, stats) and
+of size-independent properties at BASELINE.json's full sizes.  Runs on the B200 box (-m gpu)."""
+import math
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from inputs import config1_clips, short_clip, us8k_small_clips
+from parity import LOGMEL_TOL, assert_logmel_close
+
+pytestmark = pytest.mark.gpu
+AST_MEAN, AST_STD = -6.6268, 5.0613
+
+
+@pytest.fixture(scope="module")
+def b2():
+    import dl_sound_classification_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import fbank_oracle
+    return fbank_oracle
+
+
+def test_ast_preprocessor_per_clip_contract(b2, O):
+    """preprocess(waveform[1,N] CPU, sr) -> [1, n_mels, T] on the input's device (preprocessing.py:1013)."""
+    pre = b2.create_preprocessor("ast", dict(sample_rate=44100, n_mels=128, normalize=True, target_mean=0.0,
+                                             target_std=0.5, norm_mean=AST_MEAN, norm_std=AST_STD,
+                                             target_frames=512), "/tmp/unused")
+    w = config1_clips(1)[0]
+    out = pre.preprocess(w, 44100)
+    assert out.device.type == "cpu" and tuple(out.shape) == (1, 128, 512) and out.dtype == torch.float32
+    ref, m = O.ast_frontend(w[0].numpy(), 44100, target_frames=512, mean=AST_MEAN, std=AST_STD)
+    assert np.abs(out[0].numpy().T - ref).max() < LOGMEL_TOL / (2 * AST_STD) * 1.01
+    assert torch.equal(pre.preprocess_with_cache(w, 44100, None), out)
+    g = pre.preprocess(w.cuda(), 44100)
+    assert g.is_cuda and torch.equal(g.cpu(), out)
+    # natural frame count when target_frames is not configured
+    pre2 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False))
+    assert tuple(pre2.preprocess(w, 44100).shape) == (1, 128, 498)
+    # per-clip normalisation (the reference's own convention: global mean / unbiased std, * 0.5)
+    pre3 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=True))
+    x = pre3.preprocess(w, 44100)
+    assert abs(float(x.mean())) < 1e-4 and abs(float(x.std()) - 0.5) < 1e-4
+    with pytest.raises(AssertionError):
+        pre2.preprocess(torch.zeros(1, 500), 44100)            # shorter than one 25 ms window
+
+
+def test_batch_with_fused_masks_matches_sequential_reference_calls(b2, O):
+    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, norm_mean=AST_MEAN, norm_std=AST_STD,
+                                                    target_frames=512))
+    clips = config1_clips(4, length=110250)
+    random.seed(5)
+    masks = pre.draw_specaugment_masks(4, 512, 192, 48)
+    out, nfr = pre.preprocess_batch(torch.cat(clips, 0), 44100, masks=masks)
+    assert tuple(out.shape) == (4, 1, 128, 512)
+    random.seed(5)
+    for i, c in enumerate(clips):
+        plain = pre.preprocess(c, 44100)
+        want = pre.apply_specaugment(plain, 192, 48)             # the reference's call sequence (esc50.py:254-273)
+        assert torch.equal(out[i].cpu(), want), i
+        assert int(want.eq(0).sum()) > 0
+
+
+def test_multi_crop_test(b2):
+    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False))
+    w = short_clip(44100 * 7, seed=5)
+    crops = pre.multi_crop_test(w)
+    assert len(crops) == 10 and all(tuple(c.shape) == (1, 128, 498) for c in crops)
+    starts = torch.linspace(0, 44100 * 2, 10).long()
+    one = pre.preprocess(w[..., int(starts[3]):int(starts[3]) + 220500], 44100)
+    assert torch.equal(crops[3], one)
+    assert len(pre.multi_crop_test(short_clip(44100 * 2))) == 1
+
+
+def test_resample_waveform(b2, O):
+    for rate in (44100, 22050, 48000, 8000):
+        w = short_clip(rate // 2 + 37, seed=rate)
+        y = b2.resample_waveform(w, rate, 16000)
+        ref = O.resample(w[0].numpy(), rate, 16000, dtype=np.float64)
+        assert y.device.type == "cpu" and tuple(y.shape) == (1, ref.shape[0])
+        assert np.abs(y[0].numpy() - ref).max() < 3e-6, rate
+    w = short_clip(1000)
+    assert b2.resample_waveform(w, 44100, 44100) is w
+    up = b2.resample_waveform(w.cuda(), 16000, 44100)                         # the reference also upsamples (prepare_esc50.py:53-57)
+    ref = O.resample(w[0].numpy(), 16000, 44100, dtype=np.float64)
+    assert up.is_cuda and np.abs(up[0].cpu().numpy() - ref).max() < 3e-6
+    live = pytest.importorskip("torchaudio")
+    import torchaudio.transforms as T
+    w = short_clip(50000, seed=3)
+    assert np.abs(b2.resample_waveform(w, 44100, 16000).numpy() - T.Resample(44100, 16000)(w).numpy()).max() < 3e-6
+
+
+def test_dataset_stats_api(b2, O, golden):
+    g = golden("config1.npz")
+    clips = config1_clips(40)
+    fe = b2.FbankFrontend(orig_rates=(44100,), **b2.AST_FBANK_KWARGS)
+    ds = b2.DatasetStats(fe, max_frames=512)
+    wav = torch.cat(clips, 0).cuda()
+    ds.update(wav[:13]).update(wav[13:]).all_reduce()
+    st = ds.finalize()
+    rm, rs, rgm, rgs = O.stats_finalize(g["stats_sums"])
+    assert st.frames == 40 * 498
+    assert (np.abs(st.mean_per_bin.numpy() - rm) <= 1e-4 * (np.abs(rm) + rs)).all()
+    keep = np.arange(128) != 3
+    np.testing.assert_allclose(st.std_per_bin.numpy()[keep], rs[keep], rtol=1e-4)
+    assert abs(st.mean - rgm) <= 1e-4 * abs(rgm) and abs(st.std - rgs) <= 1e-4 * rgs
+    # the stats pass and the feature pass agree with each other (same kernel, different epilogue)
+    feats, _ = fe(wav, out_frames=498)
+    f64 = feats.double()
+    s = torch.cat([f64.sum((0, 1)), (f64 * f64).sum((0, 1))]).cpu().numpy()
+    np.testing.assert_allclose(ds.sums.cpu().numpy()[:256], s, rtol=1e-9, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_config2_batch1024_properties(b2, O):
+    """1024 ESC-50 clips -> (1024, 512, 128): batch invariance, pad rows, one-hop shift, gain."""
+    B, N = 1024, 220500
+    fe = b2.FbankFrontend(orig_rates=(44100,), **b2.AST_FBANK_KWARGS)
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    wav = torch.rand((B, N), generator=gen, device="cuda") * 2 - 1
+    out, nfr = fe(wav, out_frames=512, mean=AST_MEAN, std=AST_STD)
+    assert tuple(out.shape) == (B, 512, 128) and bool((nfr == 498).all())
+    assert bool(torch.isfinite(out).all())
+    pad = (0.0 - AST_MEAN) * (0.5 / AST_STD)
+    assert bool((out[:, 498:, :] - pad).abs().max() < 1e-6)
+    idx = [0, 1, 511, 777, 1023]
+    alone, _ = fe(wav[idx], out_frames=512, mean=AST_MEAN, std=AST_STD)
+    assert torch.equal(alone, out[idx])                                   # batch invariance, bit-exact
+    # a 441-sample (= one 16 kHz hop) delay shifts the features by one frame; a 4-hop delay keeps the
+    # frame pairing of the packed FFT and the lane assignment, so it is bit-exact
+    a, _ = fe(wav[:4], out_frames=512)
+    sh = torch.zeros((4, N), device="cuda")
+    sh[:, 441:] = wav[:4, :-441]
+    b_, _ = fe(sh, out_frames=512)
+    live1 = a[:, 3:497] > -12
+    assert float((b_[:, 4:498] - a[:, 3:497])[live1].abs().max()) < LOGMEL_TOL   # two float32 evaluations of the same frames
+    sh = torch.zeros((4, N), device="cuda")
+    sh[:, 4 * 441:] = wav[:4, :-4 * 441]
+    b_, _ = fe(sh, out_frames=512)
+    assert torch.equal(b_[:, 8:498], a[:, 4:494])
+    # gain 2^-3 lowers every log-mel value by 6 ln 2 (power-of-two scaling is exact in float32)
+    c_, _ = fe(wav[:4] * 0.125, out_frames=512)
+    live = a[:, :498] > -10          # stay clear of the FLT_EPSILON floor after the -4.16 shift
+    assert float(((a[:, :498] - c_[:, :498]) - 6 * math.log(2.0))[live].abs().max()) < 5e-6
+    # oracle on a sample of clips (the oracle needs ~15 ms per clip)
+    for i in (3, 500, 1023):
+        ref, _ = O.ast_frontend(wav[i].cpu().numpy(), 44100, target_frames=512, mean=AST_MEAN, std=AST_STD)
+        assert np.abs(out[i].cpu().numpy() - ref).max() < LOGMEL_TOL / (2 * AST_STD) * 1.01
+
+
+def test_config3_us8k_4096_ragged_masks(b2, O):
+    """4096 ragged clips at 22.05/44.1/48 kHz -> (4096, 1024, 128) with SpecAugment masks."""
+    B = 4096
+    table = (22050, 44100, 48000)
+    g = torch.Generator().manual_seed(31)
+    rid = torch.randint(0, 3, (B,), generator=g)
+    dur = 1.0 + 3.0 * torch.rand(B, generator=g)
+    lens = (dur * torch.tensor(table)[rid]).long()
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    gen = torch.Generator(device="cuda").manual_seed(32)
+    flat = torch.rand(int(offsets[-1]), generator=gen, device="cuda") * 2 - 1
+    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    random.seed(77)
+    masks = b2.specaugment.draw_masks(B, 1024, 128, 192, 48, variant="reference")
+    out, nfr = fe(flat, out_frames=1024, offsets=offsets, rate_ids=rid.int(), masks=masks, mean=AST_MEAN, std=AST_STD)
+    assert tuple(out.shape) == (B, 1024, 128) and bool(torch.isfinite(out).all())
+    want_frames = [fe.num_frames(int(n), int(r)) for n, r in zip(lens[:64], rid[:64])]
+    assert nfr[:64].cpu().tolist() == want_frames and int(nfr.max()) <= 398
+    # masked cells: exactly the drawn intervals, exactly 0.0 (bit-exact per seed)
+    rng = O.PyRandom(77)
+    zeros = out.eq(0)
+    for i in range(B):
+        t0, tl, f0, fl = O.specaugment_intervals_reference(rng, 1024, 128, 192, 48)
+        assert masks[i].tolist() == [t0, tl, f0, fl]
+        if i % 257 == 0:
+            z = zeros[i].cpu().numpy()
+            want = np.zeros((1024, 128), bool)
+            want[t0:t0 + tl] = True
+            want[:, f0:f0 + fl] = True
+            assert (z == want).all(), i
+    for i in (0, 1234, 4095):
+        w = flat[int(offsets[i]):int(offsets[i + 1])].cpu().numpy()
+        ref, m = O.ast_frontend(w, table[int(rid[i])], target_frames=1024, mean=AST_MEAN, std=AST_STD,
+                                mask=masks[i].tolist())
+        assert m == int(nfr[i])
+        assert np.abs(out[i].cpu().numpy() - ref).max() < LOGMEL_TOL / (2 * AST_STD) * 1.01, i
+
+
+def test_config4_stats_sharded_partials_add_up(b2, O):
+    """Stats pass over 2048 synthetic clips in 8 contiguous shards == one pass over all of them, and a
+    64-clip subset matches the float64 oracle to rel 1e-4 (the cross-rank all-reduce is a plain SUM)."""
+    from dl_sound_classification_b200 import stats as ST
+    B, N = 2048, 220500
+    fe = b2.FbankFrontend(orig_rates=(44100,), **b2.AST_FBANK_KWARGS)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    wav = torch.rand((B, N), generator=gen, device="cuda") * 2 - 1
+    whole = b2.DatasetStats(fe, 512).update(wav).sums
+    parts = torch.zeros_like(whole)
+    for r in range(8):
+        lo, hi = ST.shard_bounds(B, r, 8)
+        parts += b2.DatasetStats(fe, 512).update(wav[lo:hi]).sums
+    assert float(whole[256]) == B * 498 == float(parts[256])
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=1e-12)
+    sub = b2.DatasetStats(fe, 512).update(wav[:64]).finalize()
+    feats = [O.kaldi_fbank(O.resample(wav[i].cpu().numpy(), 44100, 16000), O.ast_fbank_options()) for i in range(64)]
+    rm, rs, rgm, rgs = O.stats_finalize(O.dataset_stats(feats))
+    assert (np.abs(sub.mean_per_bin.numpy() - rm) <= 1e-4 * (np.abs(rm) + rs)).all()
+    keep = np.arange(128) != 3
+    np.testing.assert_allclose(sub.std_per_bin.numpy()[keep], rs[keep], rtol=1e-4)
