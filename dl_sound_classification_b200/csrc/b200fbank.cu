@@ -342,7 +342,9 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     for (int j = 0; j < f.mel_maxcnt[i]; ++j)
       for (int l = 0; l < 32; ++l) {
         const int m = 32 * i + l;
-        if (m < p->n_mel && j < p->mel_cnt[m]) melw[(size_t)(f.mel_woff[i] + j) * 32 + l] = p->mel_w[p->mel_off[m] + j];
+        // the kernel leaves out the 1/4 (power) or 1/2 (magnitude) of the conjugate split: exact power-of-two fold
+        if (m < p->n_mel && j < p->mel_cnt[m])
+          melw[(size_t)(f.mel_woff[i] + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * (o.use_power ? 0.25f : 0.5f);
       }
   for (size_t ri = 0; ri < p->rates.size(); ++ri) {
     const RateHost& r = p->rates[ri];
@@ -370,7 +372,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   if (int rc = dev_copy(tw.data(), tw.size() * 4, (const void**)&f.tw)) return rc;
   if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
   const char* seg = getenv("B200FBANK_SEG");
-  f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 128;
+  f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 0;      // 0 = pick per launch (pick_seg_frames)
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
@@ -442,6 +444,15 @@ int upload(b200fbank_plan* p) {
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   return 0;
+}
+
+// Frames per CTA of the fast kernel: long segments amortise the per-segment set-up (table staging,
+// two-hop prologue), short ones keep every SM busy for small batches.  2 CTAs/SM x 148 SMs = 296 slots.
+int pick_seg_frames(const b200::FastParams& f, int B, int frames) {
+  if (f.seg_frames > 0) return f.seg_frames;
+  for (int seg = 512; seg > 32; seg >>= 1)
+    if ((int64_t)B * ((frames + seg - 1) / seg) >= 2 * 296) return seg;
+  return 32;
 }
 
 int check_device_call(const b200fbank_plan* p, const void* wav, const int64_t* offsets, int64_t clip_samples, int B) {
@@ -559,6 +570,7 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   if (cms) { k.masks = nullptr; k.n_stats = 0; }     // raw features first, cms_kernel finishes
   if (p->fast_ok) {
     b200::FastParams f = p->fast;
+    f.seg_frames = pick_seg_frames(f, B, out_frames);
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
@@ -596,6 +608,7 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
   k.max_frames = max_frames; k.sums = d_sums;
   if (p->fast_ok) {
     b200::FastParams f = p->fast;
+    f.seg_frames = pick_seg_frames(f, B, max_frames);
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");

@@ -162,7 +162,7 @@ __device__ __forceinline__ int fk_load_x_async(const float* g /* = clip + in_lo 
 struct FkLane {
   float win[13];        // window at n = lane + 32 j
   int mstart[4];        // first FFT bin of mel filters lane + 32 i
-  float nmean[4], nscale[4];
+  float nmean[4], nscale[4], nshift[4];   // epilogue: (x - nmean) * nscale + nshift (frequency mask folded in)
 };
 
 // DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.
@@ -276,8 +276,10 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       float px = __shfl_sync(0xffffffffu, oth.x, src);
       float py = __shfl_sync(0xffffffffu, oth.y, src);
       if (k1l == 0) { px = own.x; py = own.y; }
-      const float ar = zk.x + px, ai = zk.y - py, br = zk.y + py, bi = px - zk.x;
-      float pa = 0.25f * fmaf(ar, ar, ai * ai), pb = 0.25f * fmaf(br, br, bi * bi);
+      // A = (Z[k] + conj Z[N-k]) / 2, B = (Z[k] - conj Z[N-k]) / 2i; the 1/4 (1/2 for magnitudes) is folded into
+      // the mel weights on the host (exact: a power of two)
+      const float2 sm = cadd(zk, make_float2(px, py)), df = csub(zk, make_float2(px, py));
+      float pa = fmaf(sm.x, sm.x, df.y * df.y), pb = fmaf(sm.y, sm.y, df.x * df.x);
       if (!p.use_power) { pa = sqrtf(pa); pb = sqrtf(pb); }
       P2[32 * k2] = make_float2(pa, pb);
     }
@@ -285,7 +287,6 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   }
   // ---- mel (lanes = bins), log, normalise, mask, store                              // [phase: mel]
   const float4* P4 = reinterpret_cast<const float4*>(Ebuf);
-  const float tmean = p.n_stats > 0 ? p.target_mean : 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= fp.mel_groups) continue;
@@ -303,23 +304,41 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       }
     }
     if (m < p.n_mel) {                                                                 // [phase: epilogue_store]
-      float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + (r0 + f0)) * p.n_cols + m
-                               : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + (r0 + f0);
-      const int ostep = p.layout == 0 ? p.n_cols : 1;
-      const bool fmask = (m >= mk2 && m < mk2 + mk3);
+      float x[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const int t = r0 + f0 + h;
-        const bool live = (f0 + h) < nf;
-        float x = acc[h];
-        if (p.use_log) x = x > B200_FLT_EPSILON ? __logf(x) : B200_LOG_FLT_EPSILON;   // exact floor value (kaldi.py:633)
-        if (STATS) {
-          if (live) { st_s[i] += (double)x; st_ss[i] += (double)x * (double)x; }
-        } else if (t < row_end) {
-          x = live ? x : 0.f;
-          x = fmaf(x - L.nmean[i], L.nscale[i], tmean);
-          if (fmask || (t >= mk0 && t < mk0 + mk1)) x = 0.f;
-          o[h * ostep] = x;
+        x[h] = acc[h];
+        if (p.use_log) {                           // lg2.approx * ln 2; the floor value is the exact float32 log(FLT_EPSILON)
+          float l2;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(acc[h], B200_FLT_EPSILON)));
+          x[h] = acc[h] > B200_FLT_EPSILON ? l2 * 0.69314718055994531f : B200_LOG_FLT_EPSILON;
+        }
+      }
+      if (STATS) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          if ((f0 + h) < nf) { st_s[i] += (double)x[h]; st_ss[i] += (double)x[h] * (double)x[h]; }
+      } else {
+        const int t0 = r0 + f0;
+        float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + t0) * p.n_cols + m
+                                 : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + t0;
+        const int ostep = p.layout == 0 ? p.n_cols : 1;
+        // warp-uniform fast path: four live frames inside the segment and no time mask touching them
+        const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
+        if (plain) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(x[h] - L.nmean[i], L.nscale[i], L.nshift[i]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int t = t0 + h;
+            if (t < row_end) {
+              float y = (f0 + h) < nf ? x[h] : 0.f;                 // H9: pad rows are 0.0 before normalisation
+              y = fmaf(y - L.nmean[i], L.nscale[i], L.nshift[i]);
+              if (t >= mk0 && t < mk0 + mk1) y = 0.f;
+              o[h * ostep] = y;
+            }
+          }
         }
       }
     }
@@ -355,6 +374,11 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
     for (int i = tid; i < 512; i += FK_THREADS) stw[i] = __ldg(fp.tw + i);
     for (int i = tid; i < fp.mel_rows * 32; i += FK_THREADS) smelw[i] = __ldg(fp.melw + i);
   }
+  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+  if (!STATS && p.masks) {
+    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+  }
   FkLane L;
 #pragma unroll
   for (int j = 0; j < 13; ++j) L.win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
@@ -362,17 +386,14 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
   for (int i = 0; i < 4; ++i) {
     const int m = lane + 32 * i;
     L.mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
-    L.nmean[i] = 0.f; L.nscale[i] = 1.f;
+    L.nmean[i] = 0.f; L.nscale[i] = 1.f; L.nshift[i] = 0.f;
     if (!STATS && p.n_stats > 0 && m < p.n_mel) {
       const int si = p.n_stats == 1 ? 0 : m;
       L.nmean[i] = __ldg(p.mean + si);
       L.nscale[i] = p.target_std / __ldg(p.std + si);
+      L.nshift[i] = p.target_mean;
     }
-  }
-  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
-  if (!STATS && p.masks) {
-    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
-    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+    if (m >= mk2 && m < mk2 + mk3) { L.nscale[i] = 0.f; L.nshift[i] = 0.f; }   // frequency mask: the whole column is 0.0
   }
   double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
   __syncthreads();

@@ -73,12 +73,33 @@ template <int N, int I> struct BitRevI {
 B200_CHD constexpr int bitrev_n(int i, int bits) { int r = 0; for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b); return r; }
 B200_CHD constexpr int log2_n(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
 
+// Complex add / subtract.  On sm_100 each is ONE packed instruction (add.rn.f32x2 -> FADD2): Blackwell's
+// dual-FP32 path halves the issue slots of the butterfly adds.
+B200_HD float2 cadd(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+B200_HD float2 csub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+
 // One DIF stage: blocks of size 2*H starting at BASE; twiddle step = 32 / (2*H).
 template <int N, int H, int BASE, int J> struct DifButterfly {
   static B200_HD void run(float2 (&v)[N]) {
     float2 a = v[BASE + J], b = v[BASE + J + H];
-    v[BASE + J] = make_float2(a.x + b.x, a.y + b.y);
-    v[BASE + J + H] = mul_w32<J * (16 / H)>(make_float2(a.x - b.x, a.y - b.y));
+    v[BASE + J] = cadd(a, b);
+    v[BASE + J + H] = mul_w32<J * (16 / H)>(csub(a, b));
     if constexpr (J + 1 < H) DifButterfly<N, H, BASE, J + 1>::run(v);
   }
 };

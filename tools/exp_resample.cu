@@ -10,6 +10,7 @@
 #include "../dl_sound_classification_b200/csrc/taps_441_160.inc"
 
 constexpr int RP = 5, LT = 36, WIN = 46, NG = 32;
+__constant__ float c_taps[NG * 180];
 constexpr int XF = 32 * 441 + 480, RING = 34 * 161 + 2;
 
 template <int G> __device__ __forceinline__ void dispatch_imm(int g, const float* xs, float* yo) {
@@ -68,6 +69,23 @@ __device__ __forceinline__ void group_f2(const float2* __restrict__ T2, const fl
   for (int r = 0; r < RP; ++r) yo[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
 }
 
+// V3: taps through the constant bank (LDC, a path separate from the shared-memory pipe)
+__device__ __forceinline__ void group_const(int g, const float* __restrict__ xs, float* __restrict__ yo) {
+  float acc[RP] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* T = c_taps + g * 180;
+#pragma unroll
+  for (int u = 0; u < WIN; ++u) {
+    const float xv = xs[u];
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const int j = u - (r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 6 : 10);
+      if (j >= 0 && j < LT) acc[r] = fmaf(T[r * LT + j], xv, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RP; ++r) yo[r] = acc[r];
+}
+
 template <int V>
 __global__ void __launch_bounds__(256, 2) kern(const float* __restrict__ x, const float* __restrict__ taps, float* __restrict__ out, int nchunks) {
   extern __shared__ __align__(16) float smem[];
@@ -76,7 +94,7 @@ __global__ void __launch_bounds__(256, 2) kern(const float* __restrict__ x, cons
   float* st = ring + RING;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < XF; i += 256) A[i] = x[(blockIdx.x * 977 + i) % 100000];
-  if (V != 1) for (int i = tid; i < NG * 180; i += 256) st[i] = taps[i];
+  if (V == 0 || V == 2) for (int i = tid; i < NG * 180; i += 256) st[i] = taps[i];
   __syncthreads();
   float chk = 0.f;
   for (int c = 0; c < nchunks; ++c) {
@@ -87,6 +105,7 @@ __global__ void __launch_bounds__(256, 2) kern(const float* __restrict__ x, cons
       const int g = warp * 4 + gi;
       if (V == 0) group_smem(reinterpret_cast<const float4*>(st + g * 180), xl + 1 + g * 13, yl + RP * g);
       else if (V == 1) dispatch_imm<0>(g, xl, yl);
+      else if (V == 3) group_const(g, xl + 1 + g * 13, yl + RP * g);
       else group_f2(reinterpret_cast<const float2*>(st + g * 180), xl + 1 + g * 13, yl + RP * g);
     }
     __syncthreads();
@@ -98,7 +117,7 @@ __global__ void __launch_bounds__(256, 2) kern(const float* __restrict__ x, cons
 }
 
 template <int V> float run(const float* x, const float* taps, float* out, int grid, int nchunks) {
-  size_t smem = (size_t)(XF + RING + (V != 1 ? NG * 180 : 0)) * 4;
+  size_t smem = (size_t)(XF + RING + ((V == 0 || V == 2) ? NG * 180 : 0)) * 4;
   cudaFuncSetAttribute(kern<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<V><<<grid, 256, smem>>>(x, taps, out, nchunks);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -119,9 +138,12 @@ int main() {
   std::vector<float> t(NG * 180);
   for (int g = 0; g < NG; ++g) for (int r = 0; r < RP; ++r) for (int j = 0; j < LT; ++j) t[g * 180 + r * LT + j] = kImmTaps[RP * g + r][j];
   cudaMemcpy(taps, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpyToSymbol(c_taps, t.data(), t.size() * 4);
   const int grid = 296, nch = 64;
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   float m0 = run<0>(x, taps, out, grid, nch), m1 = run<1>(x, taps, out, grid, nch), m2 = run<2>(x, taps, out, grid, nch);
+  float m3 = run<3>(x, taps, out, grid, nch);
+  printf("V3 const-bank   %.3f ms  %.1f SM-cycles/frame\n", m3, m3 * 1e-3 * clk * 1e3 / (2.0 * nch * 32));
   // each SM runs 2 CTAs x nch chunks of 32 frames per launch
   auto cyc = [&](float ms) { return ms * 1e-3 * clk * 1e3 / (2.0 * nch * 32); };
   printf("clock %d kHz\nV0 smem-float4  %.3f ms  %.1f SM-cycles/frame\nV1 immediates   %.3f ms  %.1f SM-cycles/frame\nV2 smem f32x2   %.3f ms  %.1f SM-cycles/frame\n",
