@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "fbank_generic.cuh"
 #include "fbank_fast.cuh"
+#include "fbank_ws.cuh"
 #include <cstdlib>
 
 namespace {
@@ -142,6 +143,9 @@ struct b200fbank_plan {
   bool fast_ok = false;
   b200::FastParams fast;
   size_t fast_smem = 0;
+  // warp-specialised kernel (fbank_ws.cuh); shares FastParams
+  bool ws_ok = false;
+  size_t ws_smem = 0;
 };
 
 namespace {
@@ -351,8 +355,9 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     int part = FK_RING_HOPS * FK_SHIFT;
     if (!r.identity) {
       // largest staging pass whose input tile fits the x region
-      while (part > 32 && ((int64_t)(part / r.nw + 2) * r.orig + r.klen) > FK_XFLOATS - 4) part -= 32;
-      if (((int64_t)(part / r.nw + 2) * r.orig + r.klen) > FK_XFLOATS - 4) return 0;   // ratio too extreme
+      const int xcap = (FK_XFLOATS < WS_XFLOATS ? FK_XFLOATS : WS_XFLOATS) - 4;
+      while (part > 32 && ((int64_t)(part / r.nw + 2) * r.orig + r.klen) > xcap) part -= 32;
+      if (((int64_t)(part / r.nw + 2) * r.orig + r.klen) > xcap) return 0;   // ratio too extreme
     }
     f.gen_part[ri] = part;
   }
@@ -371,6 +376,46 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   if (int rc = dev_copy(k0g.data(), k0g.size() * 4, (const void**)&f.k0g)) return rc;
   if (int rc = dev_copy(tw.data(), tw.size() * 4, (const void**)&f.tw)) return rc;
   if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
+  // ---- warp-specialised kernel: register-resident taps [32][5][36], even phase offsets ----------
+  {
+    std::vector<float> wt((size_t)FK_NG * WS_GROUP_FLOATS, 0.f);
+    std::vector<int> wk(FK_NG, 0);
+    bool ok = f.fast_rate_id >= 0;
+    if (ok) {
+      const RateHost& r = p->rates[f.fast_rate_id];
+      for (int g = 0; g < FK_NG && ok; ++g) {
+        int first[FK_RP], last[FK_RP], k0 = r.klen;
+        for (int q = 0; q < FK_RP; ++q) {
+          int a = r.klen, bb = -1;
+          for (int k = 0; k < r.klen; ++k)
+            if (std::fabs(r.dense[(size_t)(FK_RP * g + q) * r.klen + k]) > 1e-25f) { a = std::min(a, k); bb = std::max(bb, k); }
+          first[q] = a; last[q] = bb;
+          k0 = std::min(k0, a - ws_off(q));
+        }
+        k0 = std::max(k0, 0);
+        wk[g] = k0;
+        for (int q = 0; q < FK_RP; ++q) {
+          const int s0 = k0 + ws_off(q);
+          if (s0 > first[q] || last[q] >= s0 + WS_LT) ok = false;
+          for (int j = 0; j < WS_LT; ++j)
+            wt[(size_t)g * WS_GROUP_FLOATS + q * WS_LT + j] = (s0 + j < r.klen) ? r.dense[(size_t)(FK_RP * g + q) * r.klen + s0 + j] : 0.f;
+        }
+        if (k0 + ws_off(FK_RP - 1) + WS_LT > r.klen + 8) ok = false;      // stays inside the staged input tile
+      }
+    }
+    const char* kenv = getenv("B200FBANK_KERNEL");
+    if (kenv && strcmp(kenv, "fast") == 0) ok = false;
+    if (int rc = dev_copy(wt.data(), wt.size() * 4, (const void**)&f.ws_taps)) return rc;
+    if (int rc = dev_copy(wk.data(), wk.size() * 4, (const void**)&f.ws_k0g)) return rc;
+    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3)) * 4 + 128;
+    // rates without the 44.1 kHz structure still run through this kernel's per-sample path
+    p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
+    f.ws_ok = p->ws_ok;
+    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  }
   const char* seg = getenv("B200FBANK_SEG");
   f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 0;      // 0 = pick per launch (pick_seg_frames)
   CUDA_TRY(cudaFuncSetAttribute(b200::fbank_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
@@ -448,10 +493,10 @@ int upload(b200fbank_plan* p) {
 
 // Frames per CTA of the fast kernel: long segments amortise the per-segment set-up (table staging,
 // two-hop prologue), short ones keep every SM busy for small batches.  2 CTAs/SM x 148 SMs = 296 slots.
-int pick_seg_frames(const b200::FastParams& f, int B, int frames) {
+int pick_seg_frames(const b200::FastParams& f, int B, int frames, int slots = 296) {
   if (f.seg_frames > 0) return f.seg_frames;
   for (int seg = 512; seg > 32; seg >>= 1)
-    if ((int64_t)B * ((frames + seg - 1) / seg) >= 2 * 296) return seg;
+    if ((int64_t)B * ((frames + seg - 1) / seg) >= 2 * slots) return seg;
   return 32;
 }
 
@@ -568,7 +613,15 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   k.target_mean = target_mean; k.target_std = target_std;
   const bool cms = p->o.subtract_mean != 0;
   if (cms) { k.masks = nullptr; k.n_stats = 0; }     // raw features first, cms_kernel finishes
-  if (p->fast_ok) {
+  if (p->fast_ok && p->ws_ok) {
+    b200::FastParams f = p->fast;
+    f.seg_frames = pick_seg_frames(f, B, out_frames, 148);
+    f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
+    const int64_t grid = (int64_t)B * f.segs;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
+    if (f.ast_bank) b200::fbank_ws_kernel<false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+    else b200::fbank_ws_kernel<false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+  } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames);
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
@@ -606,7 +659,15 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
   b200::FbankParams k = p->base;
   k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
   k.max_frames = max_frames; k.sums = d_sums;
-  if (p->fast_ok) {
+  if (p->fast_ok && p->ws_ok) {
+    b200::FastParams f = p->fast;
+    f.seg_frames = pick_seg_frames(f, B, max_frames, 148);
+    f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
+    const int64_t grid = (int64_t)B * f.segs;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
+    if (f.ast_bank) b200::fbank_ws_kernel<true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+    else b200::fbank_ws_kernel<true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+  } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, max_frames);
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;

@@ -57,6 +57,11 @@ struct FastParams {
   int gen_part[B200_MAX_RATES];   // outputs per staging pass for rates on the per-sample path
   int seg_frames, segs;
   int ast_bank;           // 1: filter lengths per group are (2,3,6,11) -> fully unrolled mel
+  // warp-specialised kernel (fbank_ws.cuh): register-resident taps, phase r of group g starts at dense
+  // index ws_k0g[g] + {0,2,4,6,10}[r] and keeps 36 taps (even offsets keep input pairs aligned for FFMA2)
+  const float* ws_taps;   // [32][5][36]
+  const int* ws_k0g;      // [32]
+  int ws_ok;
 };
 
 // Copy x[in_lo, in_lo + nx) of the clip into A[sh + i]; returns sh (0..3), chosen so that
@@ -167,17 +172,19 @@ struct FkLane {
 
 // DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.
 // yb = ring + row * 161 + lane.  Loads are unconditional: every ring row holds finite data.   // [phase: stage0_frames]
+template <int RS>     // RS = ring hop stride in floats (160 = contiguous 16 kHz samples, 161 = padded rows)
 __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, const FkLane& L, float dc_scale,
                                                float preemph, int lane, float2 (&z)[16]) {
+  constexpr int PADR = RS - FK_SHIFT;      // extra floats per hop row
   const int d0 = lane == 0 ? 0 : 1;        // j = 0: replicate pad at the frame start (kaldi.py:195-198)
-  const int d5 = lane == 0 ? 2 : 1;        // j = 5, 10: n - 1 sits in the previous hop row (stride 161)
+  const int d5 = lane == 0 ? 1 + PADR : 1; // j = 5, 10: n - 1 sits in the previous hop row
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const float* y = yb + h * FK_RING_STRIDE;
+    const float* y = yb + h * RS;
     float yv[13], s = 0.f;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
-      yv[j] = y[32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0))];
+      yv[j] = y[32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0))];
       if (j < 12) s += yv[j];
     }
     s += lane < 16 ? yv[12] : 0.f;
@@ -186,7 +193,7 @@ __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, con
     const float* y5 = y - d5;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
-      const int off = 32 * j + (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+      const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
       const float prev = (j == 0) ? y0[off] : ((j == 5 || j == 10) ? y5[off] : y[off - 1]);
       const float v = ((yv[j] - mean) - preemph * (prev - mean)) * L.win[j];
       if (h == 0) z[j].x = v; else z[j].y = v;
@@ -232,26 +239,31 @@ __device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, cons
   }
 }
 
-// One frame pass of a warp: frames f0..f0+3 of the chunk (ring rows f0..f0+5) -> 4 x n_mel outputs.
-// Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths (2,3,6,11) of the AST bank.
-template <bool STATS, bool AST>
+// One frame pass of a warp: four consecutive frames starting at output row t0, whose samples start at
+// `rows` (ring rows of stride RS; 6 rows are touched) -> 4 x n_mel outputs.  n_live = how many of the four are
+// real frames (the rest are pad rows).  Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths
+// (2,3,6,11) of the AST bank.
+template <bool STATS, bool AST, int RS>
 __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const FkLane& L,
-                                              const float* __restrict__ ring, float* __restrict__ Ebuf,
+                                              const float* __restrict__ rows, float* __restrict__ Ebuf,
                                               const float2* __restrict__ stw, const float* __restrict__ smelw,
-                                              int b, int r0, int f0, int nf, int row_end, int lane,
+                                              int b, int t0, int n_live, int row_end, int lane,
                                               int mk0, int mk1, int mk2, int mk3, double (&st_s)[4], double (&st_ss)[4]) {
   float2* EA = reinterpret_cast<float2*>(Ebuf);
   float2* EB = EA + 16 * FK_EROW;
+  constexpr int f0 = 0;
+  const int nf = n_live;
+  (void)mk2; (void)mk3;
   if (f0 < nf) {
     const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
     {
       float2 z[16];
-      fk_stage0_pair(ring + f0 * FK_RING_STRIDE + lane, L, dc_scale, p.preemph, lane, z);
+      fk_stage0_pair<RS>(rows + lane, L, dc_scale, p.preemph, lane, z);
       fk_stage1_store(z, stw, lane, EA);
     }
     {
       float2 z[16];
-      fk_stage0_pair(ring + (f0 + 2) * FK_RING_STRIDE + lane, L, dc_scale, p.preemph, lane, z);
+      fk_stage0_pair<RS>(rows + 2 * RS + lane, L, dc_scale, p.preemph, lane, z);
       fk_stage1_store(z, stw, lane, EB);
     }
     __syncwarp();
@@ -319,7 +331,6 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         for (int h = 0; h < 4; ++h)
           if ((f0 + h) < nf) { st_s[i] += (double)x[h]; st_ss[i] += (double)x[h] * (double)x[h]; }
       } else {
-        const int t0 = r0 + f0;
         float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + t0) * p.n_cols + m
                                  : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + t0;
         const int ostep = p.layout == 0 ? p.n_cols : 1;
@@ -475,8 +486,12 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
     }
 
     // ================= FFT + mel: warp w owns frames 4w .. 4w+3 of the chunk ===============
-    fk_frame_pass<STATS, AST>(p, fp, L, ring, A + warp * FK_EBUF, stw, smelw, b, r0, 4 * warp, nf, row_end, lane,
-                              mk0, mk1, mk2, mk3, st_s, st_ss);
+    {
+      int n_live = nf - 4 * warp;
+      n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
+      fk_frame_pass<STATS, AST, FK_RING_STRIDE>(p, fp, L, ring + 4 * warp * FK_RING_STRIDE, A + warp * FK_EBUF, stw, smelw,
+                                                b, r0 + 4 * warp, n_live, row_end, lane, mk0, mk1, mk2, mk3, st_s, st_ss);
+    }
     __syncthreads();      // the x|taps region (exchange / power) and the ring are reused by the next chunk   // [phase: chunk_control]
   }
 

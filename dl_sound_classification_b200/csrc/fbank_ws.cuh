@@ -1,0 +1,344 @@
+// Warp-specialised fused kernel for the AST configuration (same envelope as fbank_fast.cuh).
+//
+// One CTA per SM, 384 threads = three warpgroups working as a producer/consumer pipeline over one
+// clip segment:
+//
+//   warpgroup 0 (4 "R" warps, 232 registers/thread after setmaxnreg.inc): polyphase resampler.
+//     lane = phase group (5 phases); its 180 taps live in REGISTERS for the whole kernel, so the only
+//     shared-memory traffic of the stage is the input itself: 46 loads feed 90 packed FFMA2
+//     (fma.rn.f32x2) per 5 outputs.  In iteration i lane g works on hop (8*warp + i + skew[g]) mod 32;
+//     skew[g] = 9*(g - k0[g]) mod 32 makes the 32 lanes hit 32 distinct banks in every load (441 = 25 mod 32,
+//     25*9 = 1 mod 32), and the ring stride of 160 makes the 5-wide column stores conflict free too.
+//   warpgroups 1-2 (8 "F" warps, 136 registers/thread after setmaxnreg.dec): frame passes of
+//     fbank_fast.cuh (DC/pre-emphasis/window, packed 512-point FFT, |.|^2, mel, log, epilogue, store),
+//     pass p -> warp p mod 8.
+//
+// The 16 kHz signal lives in a shared-memory ring of three 32-hop slots (+6 mirrored rows so every pass
+// reads 6 contiguous rows); slots are handed over with mbarriers (full: 128 R arrivals, empty: 256 F
+// arrivals).  R warps stream the input chunk by chunk with cp.async; nothing intermediate touches HBM.
+#pragma once
+#include "fbank_fast.cuh"
+
+namespace b200 {
+
+constexpr int WS_THREADS = 384;
+constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;
+constexpr int WS_R_THREADS = 32 * WS_R_WARPS;
+constexpr int WS_SLOTS = 3;
+constexpr int WS_RING_ROWS = 32 * WS_SLOTS;                   // 96 hops
+constexpr int WS_MIRROR = 6;                                  // rows 96..101 repeat rows 0..5
+constexpr int WS_RING_FLOATS = (WS_RING_ROWS + WS_MIRROR) * FK_SHIFT;   // 16320
+constexpr int WS_XFLOATS = 14160;                             // 31*441 + 475 + 8 slack + 3 shift, multiple of 4
+constexpr int WS_LT = 36;                                     // taps per phase (34 non-zero + even alignment)
+constexpr int WS_GROUP_FLOATS = FK_RP * WS_LT;                // 180
+
+__host__ __device__ constexpr int ws_off(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 6 : 10; }
+
+// ---- mbarrier / named barrier / register reallocation --------------------------------------------
+__device__ __forceinline__ void ws_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WS_DONE_%=;\n"
+      "bra WS_WAIT_%=;\n"
+      "WS_DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ws_bar_r() { asm volatile("bar.sync 1, %0;" ::"n"(WS_R_THREADS) : "memory"); }
+
+// 1-D bulk copy global -> shared through the TMA unit (UBLKCP): one instruction moves the whole input chunk and
+// signals `bar` with the byte count; src/dst 16-B aligned, bytes a multiple of 16.
+__device__ __forceinline__ void ws_tma_load(float* dst_smem, const float* src_gmem, unsigned bytes, uint64_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), m = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(m) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ws_pack(float a, float b) {
+  return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ unsigned long long ws_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// One hop of one lane: 5 phases from 46 input samples; T[r][jj] = taps (2jj, 2jj+1) of phase r.   // [phase: ws_resample]
+__device__ __forceinline__ void ws_resample_hop(const float* __restrict__ xs, const unsigned long long (&T)[FK_RP][WS_LT / 2],
+                                                float (&y)[FK_RP]) {
+  unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int u = 0; u < ws_off(FK_RP - 1) + WS_LT; u += 2) {
+    const unsigned long long xp = ws_pack(xs[u], xs[u + 1]);
+#pragma unroll
+    for (int r = 0; r < FK_RP; ++r) {
+      const int j = u - ws_off(r);
+      if (j >= 0 && j < WS_LT) acc[r] = ws_fma2(xp, T[r][j >> 1], acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
+}
+
+// Alignment shift of a chunk: x[in_lo + i] lands at xbuf[sh + i], so 16-B aligned global lines are 16-B aligned
+// in shared memory.
+__device__ __forceinline__ int ws_shift(const float* g) { return (int)(((uintptr_t)g >> 2) & 3); }
+
+// R-side load of an EDGE chunk x[in_lo, in_lo+nx) (128 threads): whole lines inside the clip go through cp.async,
+// lines that straddle a clip edge are assembled by hand, samples outside the clip are zeros (the zero padding
+// of torchaudio's conv, functional.py:1424).  Interior chunks use one TMA bulk copy instead.   // [phase: ws_load]
+__device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, int nx, int sh, float* xbuf, int rt) {
+  const float* g = c.wav + in_lo;
+  const float* g0 = g - sh;                                  // 16-B aligned; slot v <-> elements i = 4v - sh + {0..3}
+  const int nvec = (nx + sh + 3) >> 2;
+  const int lo = in_lo < 0 ? (int)(-in_lo) : 0;              // first element index that exists in the clip
+  const int64_t hi64 = c.n_in - in_lo;                       // one past the last
+  const int hi = hi64 > nx + 8 ? nx + 8 : (hi64 < 0 ? 0 : (int)hi64);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(xbuf);
+  for (int v = rt; v < nvec; v += WS_R_THREADS) {
+    const int i0 = 4 * v - sh;
+    if (i0 >= lo && i0 + 4 <= hi) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * v), "l"(g0 + 4 * v) : "memory");
+    } else {
+      float4 x;
+      x.x = (i0 >= lo && i0 < hi) ? __ldg(g + i0) : 0.f;
+      x.y = (i0 + 1 >= lo && i0 + 1 < hi) ? __ldg(g + i0 + 1) : 0.f;
+      x.z = (i0 + 2 >= lo && i0 + 2 < hi) ? __ldg(g + i0 + 2) : 0.f;
+      x.w = (i0 + 3 >= lo && i0 + 3 < hi) ? __ldg(g + i0 + 3) : 0.f;
+      *reinterpret_cast<float4*>(xbuf + 4 * v) = x;
+    }
+  }
+  fk_cp_async_wait_all();
+}
+
+template <bool STATS, bool AST>
+__global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankParams p, const FastParams fp) {   // [phase: ws_setup]
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;                                            // [WS_XFLOATS] input chunk (R warps only)
+  float* ring = xbuf + WS_XFLOATS;                               // [WS_RING_FLOATS] 16 kHz samples, contiguous
+  float* ebuf = ring + WS_RING_FLOATS;                           // [8][FK_EBUF] exchange / power buffers of the F warps
+  float2* stw = reinterpret_cast<float2*>(ebuf + WS_F_WARPS * FK_EBUF);   // [512]
+  float* smelw = reinterpret_cast<float*>(stw + 512);            // [mel_rows * 32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smelw + ((fp.mel_rows * 32 + 3) & ~3));   // full[3], empty[3], xfull
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / fp.segs;
+  const int seg = blockIdx.x - b * fp.segs;
+  const ClipInfo c = clip_info(p, b);
+  const int cap = STATS ? p.max_frames : p.out_frames;
+  const int m_eff = (int)(c.m < cap ? c.m : cap);
+  const int row_begin = seg * fp.seg_frames;
+  if (row_begin >= cap) return;
+  const int row_end = (row_begin + fp.seg_frames < cap) ? row_begin + fp.seg_frames : cap;
+  if (!STATS && seg == 0 && tid == 0 && p.n_frames_out) p.n_frames_out[b] = m_eff;
+  if (STATS && row_begin >= m_eff) return;
+
+  const int rows = row_end - row_begin;
+  const int n_pass = (rows + 3) >> 2;                            // passes that own output rows
+  int n_real = m_eff - row_begin;
+  n_real = n_real < 0 ? 0 : (n_real > rows ? rows : n_real);
+  const int n_real_pass = (n_real + 3) >> 2;                     // passes with at least one real frame
+  const int last_hop = 4 * (n_real_pass - 1) + 5;                // last ring row (relative hop) any pass reads
+  const int n_chunks = n_real_pass > 0 ? last_hop / 32 + 1 : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < WS_SLOTS; ++s) {
+      ws_mbar_init(bars + s, WS_R_THREADS);                      // full[s]
+      ws_mbar_init(bars + WS_SLOTS + s, 32 * WS_F_WARPS);        // empty[s]
+    }
+    ws_mbar_init(bars + 2 * WS_SLOTS, 1);                        // xfull: TMA transaction barrier of the input chunk
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (n_real_pass > 0) {
+    for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
+    for (int i = tid; i < fp.mel_rows * 32; i += WS_THREADS) smelw[i] = __ldg(fp.melw + i);
+  }
+  __syncthreads();
+
+  if (warp < WS_R_WARPS) {
+    // =============================== R warps: resampler ==========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int rid = p.rate_id ? p.rate_id[b] : 0;
+    const bool fast = (rid == fp.fast_rate_id);
+    const int rt = tid;                                          // 0..127
+    const int g = lane;
+    unsigned long long T[FK_RP][WS_LT / 2];
+    int k0 = 0, skew = 0;
+    if (fast) {
+      const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
+#pragma unroll
+      for (int r = 0; r < FK_RP; ++r)
+#pragma unroll
+        for (int jj = 0; jj < WS_LT / 2; ++jj) {
+          const float2 t2 = __ldg(tp + r * (WS_LT / 2) + jj);
+          T[r][jj] = ws_pack(t2.x, t2.y);
+        }
+      k0 = __ldg(fp.ws_k0g + g);
+      skew = ((g - k0) * 9) & 31;
+    } else {
+#pragma unroll
+      for (int r = 0; r < FK_RP; ++r)
+#pragma unroll
+        for (int jj = 0; jj < WS_LT / 2; ++jj) T[r][jj] = 0ull;
+    }
+    unsigned x_parity = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {                      // [phase: ws_resample_loop]
+      const int slot = ch % WS_SLOTS;
+      float* rb = ring + slot * 32 * FK_SHIFT;
+      int nh = last_hop - 32 * ch + 1;                           // hops of this chunk anyone reads
+      nh = nh > 32 ? 32 : nh;
+      const int64_t hop0 = (int64_t)row_begin + 32 * ch;         // absolute hop (= 16 kHz sample / 160) of ring row 0 of the slot
+      if (fast) {
+        const int64_t in_lo = hop0 * FK_ORIG - FK_WIDTH;
+        const int nx = (nh - 1) * FK_ORIG + FK_KLEN + 8;
+        const float* gsrc = c.wav + in_lo;
+        const int sh = ws_shift(gsrc);
+        if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {           // interior chunk: one TMA bulk copy
+          if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
+          ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
+          x_parity ^= 1u;
+        } else {
+          ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+          ws_bar_r();
+        }
+        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+        const float* xs = xbuf + sh + k0;
+        if (nh > 8) {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int q = (8 * warp + i + skew) & 31;
+            float y[FK_RP];
+            ws_resample_hop(xs + q * FK_ORIG, T, y);
+            float* o = rb + q * FK_SHIFT + FK_RP * g;
+#pragma unroll
+            for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
+            if (slot == 0 && q < WS_MIRROR) {
+              float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
+#pragma unroll
+              for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
+            }
+          }
+        } else {                                                 // short tail chunk: hop = warp, warp + 4
+#pragma unroll 1
+          for (int q = warp; q < nh; q += WS_R_WARPS) {
+            float y[FK_RP];
+            ws_resample_hop(xs + q * FK_ORIG, T, y);
+            float* o = rb + q * FK_SHIFT + FK_RP * g;
+#pragma unroll
+            for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
+            if (slot == 0 && q < WS_MIRROR) {
+              float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
+#pragma unroll
+              for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
+            }
+          }
+        }
+      } else {
+        // other rates: per-sample polyphase loop (or plain copy) into the same ring slot
+        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+        const int total = nh * FK_SHIFT;
+        const int64_t s_base = hop0 * FK_SHIFT;                  // absolute resampled index of slot row 0
+        if (c.R.identity) {
+          for (int t = rt; t < total; t += WS_R_THREADS) {
+            const int64_t s = s_base + t;
+            const float v = (s < c.n_in) ? __ldg(c.wav + s) : 0.f;
+            rb[t] = v;
+            if (slot == 0 && t < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + t] = v;
+          }
+        } else {
+          const int part = fp.gen_part[rid];
+          for (int done = 0; done < total; done += part) {
+            const int cnt = (total - done < part) ? total - done : part;
+            const int64_t s0 = s_base + done;
+            const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
+            const int64_t in_lo = q_lo * c.R.orig - c.R.width;
+            const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
+            if (done > 0) ws_bar_r();
+            const int sh = ws_shift(c.wav + in_lo);
+            ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+            ws_bar_r();
+            const float* xsg = xbuf + sh;
+            for (int t = rt; t < cnt; t += WS_R_THREADS) {
+              const int64_t s = s0 + t;
+              const int64_t q = s / c.R.nw;
+              const int ph = (int)(s - q * c.R.nw);
+              const float* tpp = c.R.taps + (size_t)ph * c.R.L;
+              const float* x = xsg + (q * c.R.orig + __ldg(c.R.k0 + ph) - c.R.width - in_lo);
+              float acc = 0.f;
+              for (int j = 0; j < c.R.L; ++j) acc = fmaf(__ldg(tpp + j), x[j], acc);
+              const int rel = done + t;
+              rb[rel] = acc;
+              if (slot == 0 && rel < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + rel] = acc;
+            }
+          }
+        }
+      }
+      ws_mbar_arrive(bars + slot);                               // full[slot]: release the 32 hops to the F warps
+      ws_bar_r();                                                // everyone is done with xbuf before the next load
+    }
+  } else {
+    // =============================== F warps: frames =============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    const int wf = warp - WS_R_WARPS;
+    int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+    if (!STATS && p.masks) {
+      mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+      mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+    }
+    FkLane L;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) L.win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = lane + 32 * i;
+      L.mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
+      L.nmean[i] = 0.f; L.nscale[i] = 1.f; L.nshift[i] = 0.f;
+      if (!STATS && p.n_stats > 0 && m < p.n_mel) {
+        const int si = p.n_stats == 1 ? 0 : m;
+        L.nmean[i] = __ldg(p.mean + si);
+        L.nscale[i] = p.target_std / __ldg(p.std + si);
+        L.nshift[i] = p.target_mean;
+      }
+      if (m >= mk2 && m < mk2 + mk3) { L.nscale[i] = 0.f; L.nshift[i] = 0.f; }
+    }
+    double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
+    float* Ebuf = ebuf + wf * FK_EBUF;
+    for (int pp = wf; pp < n_pass; pp += WS_F_WARPS) {           // [phase: ws_frame_loop]
+      const int t0 = row_begin + 4 * pp;
+      int n_live = m_eff - t0;
+      n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
+      if (n_live > 0) {
+        const int chn = (4 * pp + 5) >> 5;                       // newest chunk this pass reads
+        ws_mbar_wait(bars + chn % WS_SLOTS, (unsigned)((chn / WS_SLOTS) & 1));
+      }
+      const int row = (4 * pp) % WS_RING_ROWS;
+      fk_frame_pass<STATS, AST, FK_SHIFT>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, row_end, lane,
+                                          mk0, mk1, mk2, mk3, st_s, st_ss);
+      if (pp < 8 * n_chunks) ws_mbar_arrive(bars + WS_SLOTS + (pp >> 3) % WS_SLOTS);   // empty[slot of the pass's own rows]
+    }
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        if (i < fp.mel_groups && m < p.n_mel) {
+          atomicAdd(p.sums + m, st_s[i]);
+          atomicAdd(p.sums + p.n_cols + m, st_ss[i]);
+        }
+      }
+      if (wf == 0 && lane == 0 && n_real > 0) atomicAdd(p.sums + 2 * p.n_cols, (double)n_real);
+    }
+  }
+}
+
+}  // namespace b200
