@@ -22,7 +22,8 @@
 namespace b200 {
 
 constexpr int WS_THREADS = 384;
-constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;
+constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;                // warpgroup 0 = R warps, warpgroups 1-2 = F warps (2 R + 10 F measured slower: 0.82 vs 0.75 ms)
+constexpr int WS_R_ITERS = 32 / WS_R_WARPS;                   // hops per R warp per chunk
 constexpr int WS_R_THREADS = 32 * WS_R_WARPS;
 constexpr int WS_SLOTS = 3;
 constexpr int WS_RING_ROWS = 32 * WS_SLOTS;                   // 96 hops
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #pragma unroll
     for (int s = 0; s < WS_SLOTS; ++s) {
       ws_mbar_init(bars + s, WS_R_THREADS);                      // full[s]
-      ws_mbar_init(bars + WS_SLOTS + s, 32 * WS_F_WARPS);        // empty[s]
+      ws_mbar_init(bars + WS_SLOTS + s, 32 * 8);                 // empty[s]: the 8 passes of a chunk x 32 lanes
     }
     ws_mbar_init(bars + 2 * WS_SLOTS, 1);                        // xfull: TMA transaction barrier of the input chunk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,9 +167,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   }
   __syncthreads();
 
+  // register reallocation is per warpgroup: warpgroup 0 (both R warps and F warps 0-1) grows to 232, the rest shrink
+  if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+
   if (warp < WS_R_WARPS) {
     // =============================== R warps: resampler ==========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int rid = p.rate_id ? p.rate_id[b] : 0;
     const bool fast = (rid == fp.fast_rate_id);
     const int rt = tid;                                          // 0..127
@@ -216,8 +220,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         const float* xs = xbuf + sh + k0;
         if (nh > 8) {
 #pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            const int q = (8 * warp + i + skew) & 31;
+          for (int i = 0; i < WS_R_ITERS; ++i) {
+            const int q = (WS_R_ITERS * warp + i + skew) & 31;
             float y[FK_RP];
             ws_resample_hop(xs + q * FK_ORIG, T, y);
             float* o = rb + q * FK_SHIFT + FK_RP * g;
@@ -289,7 +293,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     }
   } else {
     // =============================== F warps: frames =============================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
     const int wf = warp - WS_R_WARPS;
     int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
     if (!STATS && p.masks) {
