@@ -178,6 +178,58 @@ class FbankFrontend:
                 out.data_ptr(), self._ptr(nfr), stream))
         return out, nfr
 
+    def process_host(self, h_wav: torch.Tensor, out_frames: int, h_out: Optional[torch.Tensor] = None,
+                     chunk_clips: int = 64, n_streams: int = 3, layout: str = "btf", **kw) -> torch.Tensor:
+        """Host buffers in, host buffers out: the end-to-end form of the fused path.
+
+        ``h_wav`` is a dense ``(B, n_samples)`` float32 CPU tensor (pinned memory for full PCIe
+        speed), the result a CPU tensor (pinned when allocated here).  The batch is cut into
+        chunks that rotate over ``n_streams`` CUDA streams, so the host->device copy of chunk
+        i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
+        duplex; the kernel is ~30x faster than either copy).  Keyword arguments are those of
+        ``__call__`` (``mean``, ``std``, ``target_mean``, ``target_std``); per-clip ``masks`` are
+        sliced per chunk.
+        """
+        if self.device is None:
+            raise K.B200FbankError(K.ERR_NO_DEVICE, "host-only plan: no CPU compute path exists")
+        if h_wav.device.type != "cpu" or h_wav.dim() != 2 or h_wav.dtype != torch.float32:
+            raise ValueError("h_wav must be a dense (B, n_samples) float32 CPU tensor")
+        B, N = int(h_wav.shape[0]), int(h_wav.shape[1])
+        shape = (B, int(out_frames), self.n_cols) if layout == "btf" else (B, 1, self.n_cols, int(out_frames))
+        if h_out is None:
+            h_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        elif tuple(h_out.shape) != shape or h_out.dtype != torch.float32 or h_out.device.type != "cpu":
+            raise ValueError(f"h_out must be a float32 CPU tensor of shape {shape}")
+        masks = kw.pop("masks", None)
+        for k in ("mean", "std"):                       # upload the statistics once, not per chunk
+            if kw.get(k) is not None:
+                kw[k] = self._dev(torch.as_tensor(kw[k], dtype=torch.float32).reshape(-1), torch.float32, k)
+        chunk_clips = max(1, min(int(chunk_clips), B))
+        state = getattr(self, "_host_pipe", None)
+        key = (chunk_clips, N, shape[1:], n_streams)
+        if state is None or state["key"] != key:
+            state = dict(key=key, streams=[torch.cuda.Stream(self.device) for _ in range(n_streams)],
+                         d_wav=[torch.empty((chunk_clips, N), dtype=torch.float32, device=self.device) for _ in range(n_streams)],
+                         d_out=[torch.empty((chunk_clips,) + shape[1:], dtype=torch.float32, device=self.device)
+                                for _ in range(n_streams)])
+            self._host_pipe = state
+        cur = torch.cuda.current_stream(self.device)
+        for st in state["streams"]:
+            st.wait_stream(cur)
+        for i, lo in enumerate(range(0, B, chunk_clips)):
+            hi = min(B, lo + chunk_clips)
+            n = hi - lo
+            k = i % n_streams
+            with torch.cuda.stream(state["streams"][k]):
+                dw, do = state["d_wav"][k][:n], state["d_out"][k][:n]
+                dw.copy_(h_wav[lo:hi], non_blocking=True)
+                self(dw, out_frames, masks=None if masks is None else masks[lo:hi], layout=layout, out=do,
+                     return_n_frames=False, **kw)
+                h_out[lo:hi].copy_(do, non_blocking=True)
+        for st in state["streams"]:
+            cur.wait_stream(st)
+        return h_out
+
     def resample(self, wav: torch.Tensor, offsets: Optional[torch.Tensor] = None,
                  rate_ids: Optional[torch.Tensor] = None, out_clip_samples: Optional[int] = None) -> torch.Tensor:
         """``b200fbank_resample``: dense ``(B, n)`` -> ``(B, ceil(new*n/orig))``.  With
