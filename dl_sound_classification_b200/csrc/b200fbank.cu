@@ -362,7 +362,9 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     f.gen_part[ri] = part;
   }
   p->fast_smem = (size_t)(FK_ATFLOATS + FK_RING_FLOATS + 1024 + rows * 32) * 4;
-  f.ast_bank = (f.mel_groups == 4 && f.mel_maxcnt[0] == 2 && f.mel_maxcnt[1] == 3 && f.mel_maxcnt[2] == 6 && f.mel_maxcnt[3] == 11);
+  // the AST-specialised variants: (2,3,6,11)-tap mel groups, power spectrum, log output
+  f.ast_bank = (f.mel_groups == 4 && f.mel_maxcnt[0] == 2 && f.mel_maxcnt[1] == 3 && f.mel_maxcnt[2] == 6 && f.mel_maxcnt[3] == 11 &&
+                o.use_power && o.use_log_fbank);
   if (p->fast_smem > 113 * 1024) return 0;
   auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {
     void* d = nullptr;
@@ -712,6 +714,17 @@ int b200fbank_resample(const b200fbank_plan* p, const float* d_wav, const int64_
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+#ifdef B200_WS_TIMING
+// debug builds only: read and clear the pipeline timing counters of fbank_ws.cuh
+extern "C" int b200fbank_debug_ws_timing(unsigned long long out[8]) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, b200::g_ws_timing, sizeof z) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(b200::g_ws_timing, z, sizeof z);
+  return 0;
+}
+#endif
 
 int64_t b200fbank_launch_count(int reset) {
   int64_t n = g_launches;

@@ -21,6 +21,17 @@
 
 namespace b200 {
 
+// Optional pipeline timing (compile with -DB200_WS_TIMING): per-role cycle counters summed over all CTAs into
+// g_ws_timing[8] = {R load-wait, R empty-wait, R compute, R chunks, F full-wait, F pass, F passes, -}.
+#ifdef B200_WS_TIMING
+__device__ unsigned long long g_ws_timing[8];
+#define WS_T0() const long long t0_ = clock64()
+#define WS_TACC(slot, since) do { if (lane == 0) atomicAdd(&g_ws_timing[slot], (unsigned long long)(clock64() - (since))); } while (0)
+#else
+#define WS_T0()
+#define WS_TACC(slot, since)
+#endif
+
 constexpr int WS_THREADS = 384;
 constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;                // warpgroup 0 = R warps, warpgroups 1-2 = F warps (2 R + 10 F measured slower: 0.82 vs 0.75 ms)
 constexpr int WS_R_ITERS = 32 / WS_R_WARPS;                   // hops per R warp per chunk
@@ -197,6 +208,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         for (int jj = 0; jj < WS_LT / 2; ++jj) T[r][jj] = 0ull;
     }
     unsigned x_parity = 0;
+#ifdef B200_WS_TIMING
+    long long tc_ = 0;
+#endif
     for (int ch = 0; ch < n_chunks; ++ch) {                      // [phase: ws_resample_loop]
       const int slot = ch % WS_SLOTS;
       float* rb = ring + slot * 32 * FK_SHIFT;
@@ -208,6 +222,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         const int nx = (nh - 1) * FK_ORIG + FK_KLEN + 8;
         const float* gsrc = c.wav + in_lo;
         const int sh = ws_shift(gsrc);
+#ifdef B200_WS_TIMING
+        const long long ta_ = clock64();
+#endif
         if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {           // interior chunk: one TMA bulk copy
           if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
           ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
@@ -216,7 +233,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
           ws_bar_r();
         }
+#ifdef B200_WS_TIMING
+        const long long tb_ = clock64();
+        WS_TACC(0, ta_);
+#endif
         if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+#ifdef B200_WS_TIMING
+        tc_ = clock64();
+        WS_TACC(1, tb_);
+#endif
         const float* xs = xbuf + sh + k0;
         if (nh > 8) {
 #pragma unroll 1
@@ -288,6 +313,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           }
         }
       }
+#ifdef B200_WS_TIMING
+      if (fast) { WS_TACC(2, tc_); if (lane == 0) atomicAdd(&g_ws_timing[3], 1ull); }
+#endif
       ws_mbar_arrive(bars + slot);                               // full[slot]: release the 32 hops to the F warps
       ws_bar_r();                                                // everyone is done with xbuf before the next load
     }
@@ -321,13 +349,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       const int t0 = row_begin + 4 * pp;
       int n_live = m_eff - t0;
       n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
+#ifdef B200_WS_TIMING
+      const long long tf0_ = clock64();
+#endif
       if (n_live > 0) {
         const int chn = (4 * pp + 5) >> 5;                       // newest chunk this pass reads
         ws_mbar_wait(bars + chn % WS_SLOTS, (unsigned)((chn / WS_SLOTS) & 1));
       }
+#ifdef B200_WS_TIMING
+      const long long tf1_ = clock64();
+      WS_TACC(4, tf0_);
+#endif
       const int row = (4 * pp) % WS_RING_ROWS;
       fk_frame_pass<STATS, AST, FK_SHIFT>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, row_end, lane,
                                           mk0, mk1, mk2, mk3, st_s, st_ss);
+#ifdef B200_WS_TIMING
+      WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);
+#endif
       if (pp < 8 * n_chunks) ws_mbar_arrive(bars + WS_SLOTS + (pp >> 3) % WS_SLOTS);   // empty[slot of the pass's own rows]
     }
     if (STATS) {
