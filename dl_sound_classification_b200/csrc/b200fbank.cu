@@ -409,7 +409,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     if (kenv && strcmp(kenv, "fast") == 0) ok = false;
     if (int rc = dev_copy(wt.data(), wt.size() * 4, (const void**)&f.ws_taps)) return rc;
     if (int rc = dev_copy(wk.data(), wk.size() * 4, (const void**)&f.ws_k0g)) return rc;
-    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3)) * 4 + 128;
+    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32) * 4 + 128;
     // rates without the 44.1 kHz structure still run through this kernel's per-sample path
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;

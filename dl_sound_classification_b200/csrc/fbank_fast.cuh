@@ -168,12 +168,29 @@ struct FkLane {
   float win[13];        // window at n = lane + 32 j
   int mstart[4];        // first FFT bin of mel filters lane + 32 i
   float nmean[4], nscale[4], nshift[4];   // epilogue: (x - nmean) * nscale + nshift (frequency mask folded in)
+  __device__ __forceinline__ float w(int j) const { return win[j]; }
+  __device__ __forceinline__ int ms(int i) const { return mstart[i]; }
+  __device__ __forceinline__ float mean(int i) const { return nmean[i]; }
+  __device__ __forceinline__ float scale(int i) const { return nscale[i]; }
+  __device__ __forceinline__ float shift(int i) const { return nshift[i]; }
 };
+
+// The same constants kept in shared memory ([row][32 lanes], one copy per CTA) and re-read at each use: frees 29
+// registers per thread for the FFT's instruction-level parallelism at the price of ~70 LDS per pass.
+struct FkLaneSm {
+  const float* base;    // rows: 0..12 window, 13..16 mstart (as int bits), 17..20 mean, 21..24 scale, 25..28 shift; + lane
+  __device__ __forceinline__ float w(int j) const { return base[j * 32]; }
+  __device__ __forceinline__ int ms(int i) const { return __float_as_int(base[(13 + i) * 32]); }
+  __device__ __forceinline__ float mean(int i) const { return base[(17 + i) * 32]; }
+  __device__ __forceinline__ float scale(int i) const { return base[(21 + i) * 32]; }
+  __device__ __forceinline__ float shift(int i) const { return base[(25 + i) * 32]; }
+};
+constexpr int FK_LANE_ROWS = 29;
 
 // DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.
 // yb = ring + row * 161 + lane.  Loads are unconditional: every ring row holds finite data.   // [phase: stage0_frames]
-template <int RS>     // RS = ring hop stride in floats (160 = contiguous 16 kHz samples, 161 = padded rows)
-__device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, const FkLane& L, float dc_scale,
+template <int RS, class LC>     // RS = ring hop stride in floats (160 = contiguous 16 kHz samples, 161 = padded rows)
+__device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, const LC& L, float dc_scale,
                                                float preemph, int lane, float2 (&z)[16]) {
   constexpr int PADR = RS - FK_SHIFT;      // extra floats per hop row
   const int d0 = lane == 0 ? 0 : 1;        // j = 0: replicate pad at the frame start (kaldi.py:195-198)
@@ -195,7 +212,7 @@ __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, con
     for (int j = 0; j < 13; ++j) {
       const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
       const float prev = (j == 0) ? y0[off] : ((j == 5 || j == 10) ? y5[off] : y[off - 1]);
-      const float v = ((yv[j] - mean) - preemph * (prev - mean)) * L.win[j];
+      const float v = ((yv[j] - mean) - preemph * (prev - mean)) * L.w(j);
       if (h == 0) z[j].x = v; else z[j].y = v;
     }
   }
@@ -243,8 +260,8 @@ __device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, cons
 // `rows` (ring rows of stride RS; 6 rows are touched) -> 4 x n_mel outputs.  n_live = how many of the four are
 // real frames (the rest are pad rows).  Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths
 // (2,3,6,11) of the AST bank.
-template <bool STATS, bool AST, int RS>
-__device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const FkLane& L,
+template <bool STATS, bool AST, int RS, class LC>
+__device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const LC& L,
                                               const float* __restrict__ rows, float* __restrict__ Ebuf,
                                               const float2* __restrict__ stw, const float* __restrict__ smelw,
                                               int b, int t0, int n_live, int row_end, int lane,
@@ -261,7 +278,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
 #pragma unroll
     for (int tr = 0; tr < 2; ++tr) {
       float2 z[16];
-      fk_stage0_pair<RS>(rows + 2 * tr * RS + lane, L, dc_scale, p.preemph, lane, z);
+      fk_stage0_pair<RS, LC>(rows + 2 * tr * RS + lane, L, dc_scale, p.preemph, lane, z);
       fk_stage1_store(z, stw, lane, tr == 0 ? EA : EB);
     }
     __syncwarp();
@@ -305,12 +322,12 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
     if (f0 < nf) {
       const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
       if (AST) {
-        if (i == 0) fk_mel_group<2>(P4, wrow, L.mstart[i], 0, acc);
-        else if (i == 1) fk_mel_group<3>(P4, wrow, L.mstart[i], 0, acc);
-        else if (i == 2) fk_mel_group<6>(P4, wrow, L.mstart[i], 0, acc);
-        else fk_mel_group<11>(P4, wrow, L.mstart[i], 0, acc);
+        if (i == 0) fk_mel_group<2>(P4, wrow, L.ms(i), 0, acc);
+        else if (i == 1) fk_mel_group<3>(P4, wrow, L.ms(i), 0, acc);
+        else if (i == 2) fk_mel_group<6>(P4, wrow, L.ms(i), 0, acc);
+        else fk_mel_group<11>(P4, wrow, L.ms(i), 0, acc);
       } else {
-        fk_mel_group<-1>(P4, wrow, L.mstart[i], fp.mel_maxcnt[i], acc);
+        fk_mel_group<-1>(P4, wrow, L.ms(i), fp.mel_maxcnt[i], acc);
       }
     }
     if (m < p.n_mel) {                                                                 // [phase: epilogue_store]
@@ -336,14 +353,14 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
         if (plain) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(x[h] - L.nmean[i], L.nscale[i], L.nshift[i]);
+          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(x[h] - L.mean(i), L.scale(i), L.shift(i));
         } else {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const int t = t0 + h;
             if (t < row_end) {
               float y = (f0 + h) < nf ? x[h] : 0.f;                 // H9: pad rows are 0.0 before normalisation
-              y = fmaf(y - L.nmean[i], L.nscale[i], L.nshift[i]);
+              y = fmaf(y - L.mean(i), L.scale(i), L.shift(i));
               if (t >= mk0 && t < mk0 + mk1) y = 0.f;
               o[h * ostep] = y;
             }
@@ -487,7 +504,7 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
     {
       int n_live = nf - 4 * warp;
       n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
-      fk_frame_pass<STATS, AST, FK_RING_STRIDE>(p, fp, L, ring + 4 * warp * FK_RING_STRIDE, A + warp * FK_EBUF, stw, smelw,
+      fk_frame_pass<STATS, AST, FK_RING_STRIDE, FkLane>(p, fp, L, ring + 4 * warp * FK_RING_STRIDE, A + warp * FK_EBUF, stw, smelw,
                                                 b, r0 + 4 * warp, n_live, row_end, lane, mk0, mk1, mk2, mk3, st_s, st_ss);
     }
     __syncthreads();      // the x|taps region (exchange / power) and the ring are reused by the next chunk   // [phase: chunk_control]

@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   float* ebuf = ring + WS_RING_FLOATS;                           // [8][FK_EBUF] exchange / power buffers of the F warps
   float2* stw = reinterpret_cast<float2*>(ebuf + WS_F_WARPS * FK_EBUF);   // [512]
   float* smelw = reinterpret_cast<float*>(stw + 512);            // [mel_rows * 32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smelw + ((fp.mel_rows * 32 + 3) & ~3));   // full[3], empty[3], xfull
+  float* slane = smelw + ((fp.mel_rows * 32 + 3) & ~3);          // [FK_LANE_ROWS][32] per-lane constants of the F warps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slane + FK_LANE_ROWS * 32);   // full[3], empty[3], xfull
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / fp.segs;
@@ -176,17 +177,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
     for (int i = tid; i < fp.mel_rows * 32; i += WS_THREADS) smelw[i] = __ldg(fp.melw + i);
   }
+  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+  if (!STATS && p.masks) {
+    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+  }
+  if (tid < 32) {                                                 // lane constants: one copy per CTA (= per clip)
+    for (int j = 0; j < 13; ++j) slane[j * 32 + lane] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int m = lane + 32 * i;
+      float mean = 0.f, scale = 1.f, shift = 0.f;
+      if (!STATS && p.n_stats > 0 && m < p.n_mel) {
+        const int si = p.n_stats == 1 ? 0 : m;
+        mean = __ldg(p.mean + si);
+        scale = p.target_std / __ldg(p.std + si);
+        shift = p.target_mean;
+      }
+      if (m >= mk2 && m < mk2 + mk3) { scale = 0.f; shift = 0.f; }     // frequency mask: the whole column is 0.0
+      slane[(13 + i) * 32 + lane] = __int_as_float((m < p.n_mel) ? __ldg(p.mel_start + m) : 0);
+      slane[(17 + i) * 32 + lane] = mean;
+      slane[(21 + i) * 32 + lane] = scale;
+      slane[(25 + i) * 32 + lane] = shift;
+    }
+  }
   __syncthreads();
 
   // register reallocation is per warpgroup: warpgroup 0 (both R warps and F warps 0-1) grows to 232, the rest shrink
-  if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  // R warps are warpgroup 0 (putting them last, where the issue arbiter would favour them, measured 3% slower:
+  // the pipeline is balanced and latency-bound, not R-bound)
+  const bool is_r = warp < WS_R_WARPS;
+  if (is_r) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
 
-  if (warp < WS_R_WARPS) {
+  if (is_r) {
     // =============================== R warps: resampler ==========================================
     const int rid = p.rate_id ? p.rate_id[b] : 0;
     const bool fast = (rid == fp.fast_rate_id);
     const int rt = tid;                                          // 0..127
+    const int rw = warp;                                         // R warp index
     const int g = lane;
     unsigned long long T[FK_RP][WS_LT / 2];
     int k0 = 0, skew = 0;
@@ -246,7 +274,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         if (nh > 8) {
 #pragma unroll 1
           for (int i = 0; i < WS_R_ITERS; ++i) {
-            const int q = (WS_R_ITERS * warp + i + skew) & 31;
+            const int q = (WS_R_ITERS * rw + i + skew) & 31;
             float y[FK_RP];
             ws_resample_hop(xs + q * FK_ORIG, T, y);
             float* o = rb + q * FK_SHIFT + FK_RP * g;
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           }
         } else {                                                 // short tail chunk: hop = warp, warp + 4
 #pragma unroll 1
-          for (int q = warp; q < nh; q += WS_R_WARPS) {
+          for (int q = rw; q < nh; q += WS_R_WARPS) {
             float y[FK_RP];
             ws_resample_hop(xs + q * FK_ORIG, T, y);
             float* o = rb + q * FK_SHIFT + FK_RP * g;
@@ -322,26 +350,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   } else {
     // =============================== F warps: frames =============================================
     const int wf = warp - WS_R_WARPS;
-    int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
-    if (!STATS && p.masks) {
-      mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
-      mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
-    }
-    FkLane L;
+    FkLane L;                                                    // registers (a shared-memory copy measured 3% slower)
 #pragma unroll
-    for (int j = 0; j < 13; ++j) L.win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
+    for (int j = 0; j < 13; ++j) L.win[j] = slane[j * 32 + lane];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int m = lane + 32 * i;
-      L.mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
-      L.nmean[i] = 0.f; L.nscale[i] = 1.f; L.nshift[i] = 0.f;
-      if (!STATS && p.n_stats > 0 && m < p.n_mel) {
-        const int si = p.n_stats == 1 ? 0 : m;
-        L.nmean[i] = __ldg(p.mean + si);
-        L.nscale[i] = p.target_std / __ldg(p.std + si);
-        L.nshift[i] = p.target_mean;
-      }
-      if (m >= mk2 && m < mk2 + mk3) { L.nscale[i] = 0.f; L.nshift[i] = 0.f; }
+      L.mstart[i] = __float_as_int(slane[(13 + i) * 32 + lane]);
+      L.nmean[i] = slane[(17 + i) * 32 + lane]; L.nscale[i] = slane[(21 + i) * 32 + lane]; L.nshift[i] = slane[(25 + i) * 32 + lane];
     }
     double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
     float* Ebuf = ebuf + wf * FK_EBUF;
@@ -361,7 +376,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       WS_TACC(4, tf0_);
 #endif
       const int row = (4 * pp) % WS_RING_ROWS;
-      fk_frame_pass<STATS, AST, FK_SHIFT>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, row_end, lane,
+      fk_frame_pass<STATS, AST, FK_SHIFT, FkLane>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, row_end, lane,
                                           mk0, mk1, mk2, mk3, st_s, st_ss);
 #ifdef B200_WS_TIMING
       WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);
