@@ -6,14 +6,14 @@ in ``include/b200fbank.h``.  Importing the package loads ``lib/libb200fbank.so``
 raises if the library has not been built -- there is no CPU fallback.
 """
 from . import _capi
-from .frontend import AST_FBANK_KWARGS, FbankFrontend, launch_count
+from .frontend import AST_FBANK_KWARGS, FbankFrontend, MelSpecFrontend, launch_count
 from .kaldi import fbank
 from .preprocessing import (ASTPreprocessor, B200ASTPreprocessor, BasePreprocessor, PreprocessingConfig,
-                            create_preprocessor, resample_waveform)
+                            create_preprocessor, melspectrogram, resample_waveform)
 from .specaugment import SpecAugment
 from .stats import DatasetStats, NormStats, finalize_sums
 
 __all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi", "ASTPreprocessor",
            "B200ASTPreprocessor", "BasePreprocessor", "PreprocessingConfig", "create_preprocessor",
-           "resample_waveform", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums"]
+           "resample_waveform", "melspectrogram", "MelSpecFrontend", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums"]
 __version__ = "0.1.0"

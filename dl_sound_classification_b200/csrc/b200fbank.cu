@@ -126,7 +126,7 @@ double vtln_warp_freq(double vl, double vh, double lo, double hi, double warp, d
 struct b200fbank_plan {
   b200fbank_opts o;
   int device = -1;
-  int shift = 0, size = 0, padded = 0, log2n = 0, n_mel = 0, n_cols = 0;
+  int shift = 0, size = 0, padded = 0, log2n = 0, n_mel = 0, n_cols = 0, frame_mode = 0;
   std::vector<RateHost> rates;
   std::vector<float> window;          // [size]
   std::vector<float> mel_dense;       // [n_mel][padded/2]
@@ -153,14 +153,22 @@ namespace {
 int build_tables(b200fbank_plan* p) {
   const b200fbank_opts& o = p->o;
   // _get_waveform_and_window_properties, kaldi.py:125-151 (same float64 expression order)
+  const bool melspec = o.frontend == B200FBANK_FRONTEND_MELSPEC_DB;
   p->shift = (int)(o.sample_frequency * o.frame_shift * 0.001);
   p->size = (int)(o.sample_frequency * o.frame_length * 0.001);
+  if (melspec) {     // MelSpectrogram(n_fft, win_length, hop_length), torchaudio/transforms/_transforms.py:515-631
+    p->shift = o.hop_length;
+    p->size = o.win_length > 0 ? o.win_length : o.n_fft;
+    if (o.n_fft < 2 || (o.n_fft & (o.n_fft - 1))) return fail(B200FBANK_ERR_UNSUPPORTED, "n_fft %d: only power-of-two FFT sizes are implemented", o.n_fft);
+    if (p->size > o.n_fft) return fail(B200FBANK_ERR_INVALID, "win_length %d must be <= n_fft %d", p->size, o.n_fft);
+  }
   if (o.sample_frequency <= 0) return fail(B200FBANK_ERR_INVALID, "`sample_frequency` must be greater than zero");
   if (p->size < 2) return fail(B200FBANK_ERR_INVALID, "choose a window size %d that is [2, len(waveform)]", p->size);
   if (p->shift <= 0) return fail(B200FBANK_ERR_INVALID, "`window_shift` must be greater than 0");
   int pow2 = 1;
   while (pow2 < p->size) pow2 <<= 1;
   p->padded = o.round_to_power_of_two ? pow2 : p->size;
+  if (melspec) { p->padded = o.n_fft; pow2 = o.n_fft; }
   if (p->padded % 2 != 0)
     return fail(B200FBANK_ERR_INVALID, "the padded `window_size` must be divisible by two. use `round_to_power_of_two` or change `frame_length`");
   if (p->padded != pow2)
@@ -171,14 +179,16 @@ int build_tables(b200fbank_plan* p) {
   if (!(o.preemphasis_coefficient >= 0.0 && o.preemphasis_coefficient <= 1.0))
     return fail(B200FBANK_ERR_INVALID, "`preemphasis_coefficient` must be between [0,1]");
   if (o.energy_floor < 0.0) return fail(B200FBANK_ERR_INVALID, "energy_floor must be >= 0");
-  if (o.frontend != B200FBANK_FRONTEND_KALDI_FBANK)
-    return fail(B200FBANK_ERR_UNSUPPORTED, "frontend %d not implemented", o.frontend);
+  if (o.frontend != B200FBANK_FRONTEND_KALDI_FBANK && !melspec)
+    return fail(B200FBANK_ERR_INVALID, "unknown frontend %d", o.frontend);
+  p->frame_mode = melspec ? 2 : (o.snip_edges ? 0 : 1);
 
   // window, kaldi.py:86-113
   p->window.resize(p->size);
   const double a = 2.0 * M_PI / (p->size - 1);
   for (int i = 0; i < p->size; ++i) {
     double w;
+    if (melspec) { p->window[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / p->size)); continue; }   // torch.hann_window (periodic)
     switch (o.window_type) {
       case B200FBANK_WINDOW_HANNING: w = 0.5 - 0.5 * std::cos(a * i); break;
       case B200FBANK_WINDOW_HAMMING: w = 0.54 - 0.46 * std::cos(a * i); break;
@@ -202,9 +212,39 @@ int build_tables(b200fbank_plan* p) {
   // get_mel_banks, kaldi.py:436-511, evaluated in float64
   p->n_mel = o.num_mel_bins;
   if (p->n_mel <= 3) return fail(B200FBANK_ERR_INVALID, "Must have at least 3 mel bins");
-  p->n_cols = p->n_mel + (o.use_energy ? 1 : 0);
+  p->n_cols = p->n_mel + ((o.use_energy && !melspec) ? 1 : 0);
+  if (melspec) {
+    // melscale_fbanks(n_fft/2+1, f_min=0, f_max=sr//2, n_mels, sr, norm=None, "htk"), functional.py:518-587, in float64.
+    // The Nyquist bin gets weight 0 from every filter (the last triangle ends at f_max), so n_fft/2 bins suffice.
+    const int NBm = N / 2, n_freqs = NBm + 1;
+    const double f_max = (double)((int)o.sample_frequency / 2);
+    const double m_min = 2595.0 * std::log10(1.0 + 0.0 / 700.0), m_max = 2595.0 * std::log10(1.0 + f_max / 700.0);
+    std::vector<double> f_pts(p->n_mel + 2);
+    for (int i = 0; i < p->n_mel + 2; ++i) {
+      const double m = m_min + (m_max - m_min) * i / (p->n_mel + 1);
+      f_pts[i] = 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
+    }
+    p->mel_dense.assign((size_t)p->n_mel * NBm, 0.f);
+    p->mel_start.resize(p->n_mel); p->mel_cnt.resize(p->n_mel); p->mel_off.resize(p->n_mel);
+    p->mel_w.clear();
+    for (int m = 0; m < p->n_mel; ++m) {
+      int first = NBm, last = -1;
+      for (int k = 0; k < NBm; ++k) {
+        const double f = f_max * k / (n_freqs - 1);
+        const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]), up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+        const float wf = (float)std::max(0.0, std::min(down, up));
+        p->mel_dense[(size_t)m * NBm + k] = wf;
+        if (wf != 0.f) { first = std::min(first, k); last = std::max(last, k); }
+      }
+      p->mel_off[m] = (int)p->mel_w.size();
+      if (last < 0) { p->mel_start[m] = 0; p->mel_cnt[m] = 0; continue; }
+      p->mel_start[m] = first; p->mel_cnt[m] = last - first + 1;
+      for (int k = first; k <= last; ++k) p->mel_w.push_back(p->mel_dense[(size_t)m * NBm + k]);
+    }
+  }
   const double nyquist = 0.5 * o.sample_frequency;
   double high = o.high_freq, low = o.low_freq;
+  if (melspec) { low = 0.0; high = nyquist; }
   if (high <= 0.0) high += nyquist;
   if (!((0.0 <= low && low < nyquist) && (0.0 < high && high <= nyquist) && (low < high)))
     return fail(B200FBANK_ERR_INVALID, "Bad values in options: low-freq %g and high-freq %g vs. nyquist %g", low, high, nyquist);
@@ -216,10 +256,12 @@ int build_tables(b200fbank_plan* p) {
   const bool warp = o.vtln_warp != 1.0;
   if (warp && !((low < o.vtln_low && o.vtln_low < high) && (0.0 < vh && vh < high) && (o.vtln_low < vh)))
     return fail(B200FBANK_ERR_INVALID, "Bad values in options: vtln-low %g and vtln-high %g, versus low-freq %g and high-freq %g", o.vtln_low, vh, low, high);
-  p->mel_dense.assign((size_t)p->n_mel * NB, 0.f);
-  p->mel_start.resize(p->n_mel); p->mel_cnt.resize(p->n_mel); p->mel_off.resize(p->n_mel);
-  p->mel_w.clear();
-  for (int m = 0; m < p->n_mel; ++m) {
+  if (!melspec) {
+    p->mel_dense.assign((size_t)p->n_mel * NB, 0.f);
+    p->mel_start.resize(p->n_mel); p->mel_cnt.resize(p->n_mel); p->mel_off.resize(p->n_mel);
+    p->mel_w.clear();
+  }
+  for (int m = 0; m < p->n_mel && !melspec; ++m) {
     double left = mel_low + m * delta, center = mel_low + (m + 1.0) * delta, right = mel_low + (m + 2.0) * delta;
     if (warp) {
       left = mel_scale(vtln_warp_freq(o.vtln_low, vh, low, high, o.vtln_warp, inv_mel_scale(left)));
@@ -283,6 +325,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   p->fast_ok = false;
   const char* env = getenv("B200FBANK_KERNEL");
   if (env && strcmp(env, "generic") == 0) return 0;
+  if (o.frontend != B200FBANK_FRONTEND_KALDI_FBANK) return 0;
   if (!(p->size == FK_SIZE && p->shift == FK_SHIFT && p->padded == FK_N && o.snip_edges && !o.use_energy &&
         p->n_mel <= 128))
     return 0;
@@ -462,9 +505,11 @@ int upload(b200fbank_plan* p) {
                                (const float*)(d + o_taps[i]), (const int*)(d + o_k0[i])};
   }
   k.shift = p->shift; k.size = p->size; k.padded = p->padded; k.log2n = p->log2n;
-  k.snip_edges = o.snip_edges; k.remove_dc = o.remove_dc_offset; k.raw_energy = o.raw_energy;
-  k.use_energy = o.use_energy; k.htk_compat = o.htk_compat; k.use_power = o.use_power; k.use_log = o.use_log_fbank;
-  k.preemph = (float)o.preemphasis_coefficient;
+  const bool melspec = o.frontend == B200FBANK_FRONTEND_MELSPEC_DB;
+  k.frame_mode = p->frame_mode; k.db_mode = melspec ? 1 : 0;
+  k.snip_edges = p->frame_mode == 0; k.remove_dc = melspec ? 0 : o.remove_dc_offset; k.raw_energy = o.raw_energy;
+  k.use_energy = melspec ? 0 : o.use_energy; k.htk_compat = o.htk_compat; k.use_power = melspec ? 1 : o.use_power; k.use_log = o.use_log_fbank;
+  k.preemph = melspec ? 0.f : (float)o.preemphasis_coefficient;
   k.has_energy_floor = o.energy_floor != 0.0;
   k.log_energy_floor = k.has_energy_floor ? (float)std::log(o.energy_floor) : 0.f;
   k.window = (const float*)(d + o_win);
@@ -562,7 +607,7 @@ int64_t b200fbank_resampled_length(const b200fbank_plan* p, int64_t n, int rate_
 int64_t b200fbank_num_frames(const b200fbank_plan* p, int64_t n, int rate_id) {
   int64_t n_rs = b200fbank_resampled_length(p, n, rate_id);
   if (n_rs < 0) return n_rs;
-  return b200::num_frames(n_rs, p->size, p->shift, p->o.snip_edges);
+  return b200::num_frames(n_rs, p->size, p->shift, p->frame_mode);
 }
 
 int b200fbank_num_cols(const b200fbank_plan* p) { return p ? p->n_cols : fail(B200FBANK_ERR_INVALID, "plan is NULL"); }
@@ -601,6 +646,7 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   if (rc) return rc;
   if (out_frames <= 0) return fail(B200FBANK_ERR_INVALID, "out_frames must be > 0");
   if (layout != B200FBANK_LAYOUT_BTF && layout != B200FBANK_LAYOUT_BFT) return fail(B200FBANK_ERR_INVALID, "bad layout %d", layout);
+  if (p->o.frontend != B200FBANK_FRONTEND_KALDI_FBANK) return fail(B200FBANK_ERR_INVALID, "plan was created for the MELSPEC_DB frontend: call b200fbank_melspec_db");
   if (n_stats != 0 && n_stats != 1 && n_stats != p->n_cols)
     return fail(B200FBANK_ERR_INVALID, "n_stats must be 0, 1 or n_cols=%d (got %d)", p->n_cols, n_stats);
   if (n_stats != 0 && (!d_mean || !d_std)) return fail(B200FBANK_ERR_INVALID, "d_mean/d_std are NULL");
@@ -642,6 +688,48 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   if (cms) {
     k.masks = d_masks; k.n_stats = n_stats;
     b200::cms_kernel<<<B, 128, 0, st>>>(k);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets, int64_t clip_samples,
+                         const int32_t* d_rate_id, int B, const int32_t* d_masks, int to_db, int normalize,
+                         float target_mean, float target_std, int out_frames, int layout, float* d_out,
+                         int32_t* d_n_frames, float* d_clip_max, void* stream) {
+  int rc = check_device_call(p, d_wav, d_offsets, clip_samples, B);
+  if (rc) return rc;
+  if (p->o.frontend != B200FBANK_FRONTEND_MELSPEC_DB) return fail(B200FBANK_ERR_INVALID, "plan was not created for the MELSPEC_DB frontend");
+  if (out_frames <= 0) return fail(B200FBANK_ERR_INVALID, "out_frames must be > 0");
+  if (layout != B200FBANK_LAYOUT_BTF && layout != B200FBANK_LAYOUT_BFT) return fail(B200FBANK_ERR_INVALID, "bad layout %d", layout);
+  if (!d_out) return fail(B200FBANK_ERR_INVALID, "d_out is NULL");
+  if (to_db && !d_clip_max) return fail(B200FBANK_ERR_INVALID, "d_clip_max ([B] floats of workspace) is NULL");
+  if (!to_db && normalize) return fail(B200FBANK_ERR_INVALID, "normalize requires to_db (the reference normalises dB values)");
+  if (B == 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  b200::FbankParams k = p->base;
+  k.wav = d_wav; k.offsets = d_offsets; k.clip_samples = clip_samples; k.rate_id = d_rate_id; k.B = B;
+  k.out_frames = out_frames; k.layout = layout; k.out = d_out; k.n_frames_out = d_n_frames;
+  k.masks = nullptr; k.n_stats = 0; k.target_mean = target_mean; k.target_std = target_std;
+  k.db_mode = to_db ? 1 : 0; k.use_log = 0;
+  k.clip_max = to_db ? d_clip_max : nullptr;
+  if (to_db) {      // -inf: the ordered-int atomicMax identity
+    static const unsigned kNegInf = 0xff800000u;
+    CUDA_TRY(cudaMemsetAsync(d_clip_max, 0, sizeof(float) * B, st));
+    b200::fill_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned*>(d_clip_max), kNegInf, B);
+    ++g_launches;
+  }
+  k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
+  const int64_t grid = (int64_t)B * k.tiles;
+  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+  b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (to_db || d_masks) {
+    k.masks = d_masks;
+    b200::melspec_finalize_kernel<<<B, 256, 0, st>>>(k, to_db ? (float)p->o.top_db : -1.f, normalize);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
   }

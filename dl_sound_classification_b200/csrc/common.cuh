@@ -36,6 +36,9 @@ struct FbankParams {
   // framing (torchaudio/compliance/kaldi.py:125-151)
   int shift, size, padded, log2n;
   int snip_edges, remove_dc, raw_energy, use_energy, htk_compat, use_power, use_log;
+  int frame_mode;            // 0 snip_edges, 1 kaldi mirrored, 2 stft centred reflect (snip_edges == (frame_mode == 0))
+  int db_mode;               // 1: epilogue = 10*log10(max(x, 1e-10)) and a per-clip running maximum (AmplitudeToDB)
+  float* clip_max;           // db_mode: [B] per-clip maximum of the dB values (ordered-int atomicMax)
   float preemph, log_energy_floor; int has_energy_floor;
   const float* window;       // [size]
   const float2* twiddle;     // [padded/2]  W_N^k = (cos 2 pi k/N, -sin 2 pi k/N)
@@ -62,16 +65,29 @@ __host__ __device__ inline int64_t resampled_length(int64_t n, int orig, int nw)
   return (n * (int64_t)nw + orig - 1) / orig;
 }
 
-__host__ __device__ inline int64_t num_frames(int64_t n, int size, int shift, int snip_edges) {
-  // _get_strided, kaldi.py:63-69
-  if (snip_edges) return n < size ? 0 : 1 + (n - size) / shift;
-  return (n + shift / 2) / shift;
+// Framing modes.  0: kaldi snip_edges=True; 1: kaldi snip_edges=False (mirrored edges, kaldi.py:70-80);
+// 2: torch.stft(center=True, pad_mode="reflect") as used by MelSpectrogram (torchaudio/functional/functional.py:123-137).
+__host__ __device__ inline int64_t num_frames(int64_t n, int size, int shift, int frame_mode) {
+  if (frame_mode == 0) return n < size ? 0 : 1 + (n - size) / shift;     // _get_strided, kaldi.py:63-69
+  if (frame_mode == 1) return (n + shift / 2) / shift;
+  return 1 + n / shift;                                                  // stft: 1 + floor((n + 2*(n_fft/2) - n_fft) / hop)
+}
+
+// First (virtual) sample of frame 0.  Mode 2: the win_length window sits in the middle of the n_fft buffer, so its
+// non-zero part starts win/2 before the frame centre; |DFT|^2 does not depend on where the zeros are.
+__host__ __device__ inline int frame_offset(int size, int shift, int frame_mode) {
+  return frame_mode == 0 ? 0 : (frame_mode == 1 ? -(size / 2 - shift / 2) : -(size / 2));
 }
 
 // Virtual sample index -> real index for snip_edges=False (kaldi.py:70-80): the signal is
 // mirrored about -1/2 on the left and about n-1/2 on the right.
-__host__ __device__ inline int64_t reflect_index(int64_t v, int64_t n) {
-  if (v < 0) return -1 - v;
+__host__ __device__ inline int64_t reflect_index(int64_t v, int64_t n, int frame_mode = 1) {
+  if (frame_mode == 2) {            // torch 'reflect': [2,1,0,1,2] -- the edge sample is not repeated
+    if (v < 0) return -v;
+    if (v >= n) return 2 * n - 2 - v;
+    return v;
+  }
+  if (v < 0) return -1 - v;         // kaldi: [1,0,0,1] -- mirrored about -1/2 and n-1/2
   if (v >= n) return 2 * n - 1 - v;
   return v;
 }

@@ -27,7 +27,7 @@ __device__ inline ClipInfo clip_info(const FbankParams& p, int b) {
   int r = p.rate_id ? p.rate_id[b] : 0;
   c.R = p.rates[r];
   c.n_rs = c.R.identity ? c.n_in : resampled_length(c.n_in, c.R.orig, c.R.nw);
-  c.m = num_frames(c.n_rs, p.size, p.shift, p.snip_edges);
+  c.m = num_frames(c.n_rs, p.size, p.shift, p.frame_mode);
   return c;
 }
 
@@ -95,6 +95,12 @@ __device__ inline void stage_resampled(const ClipInfo& c, int64_t s_lo, int64_t 
   __syncthreads();
 }
 
+// atomicMax on a float through the ordered-integer view (valid for any finite mix of signs)
+__device__ inline void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 __device__ inline float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -139,14 +145,14 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
     // ---- H1 + H3: stage the resampled samples this tile's frames touch ------------------
     int64_t v_lo = (int64_t)t0 * p.shift, v_hi = (int64_t)(f_end - 1) * p.shift + p.size;
     int64_t s_lo = v_lo, s_hi = v_hi;
-    if (!p.snip_edges) {
-      const int64_t pad = p.size / 2 - p.shift / 2;
-      v_lo -= pad; v_hi -= pad;
-      // hull of the mirrored index set {reflect(v) : v_lo <= v < v_hi}; never longer than the span
+    if (p.frame_mode != 0) {
+      const int64_t fo = frame_offset(p.size, p.shift, p.frame_mode);
+      v_lo += fo; v_hi += fo;
+      // hull of the mirrored index set {reflect(v) : v_lo <= v < v_hi}; at most one sample longer than the span
       s_lo = v_lo < 0 ? 0 : v_lo;
       s_hi = v_hi > c.n_rs ? c.n_rs : v_hi;
-      if (v_hi > c.n_rs && 2 * c.n_rs - v_hi < s_lo) s_lo = 2 * c.n_rs - v_hi;
-      if (v_lo < 0 && -v_lo > s_hi) s_hi = -v_lo;
+      if (v_hi > c.n_rs) { const int64_t r = reflect_index(v_hi - 1, c.n_rs, p.frame_mode); if (r < s_lo) s_lo = r; }
+      if (v_lo < 0) { const int64_t r = reflect_index(v_lo, c.n_rs, p.frame_mode) + 1; if (r > s_hi) s_hi = r; }
       if (s_lo < 0) s_lo = 0;
       if (s_hi > c.n_rs) s_hi = c.n_rs;
     }
@@ -161,11 +167,11 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
       for (int h = 0; h < 2; ++h) {
         int f = t0 + 2 * g + h;
         live[h] = f < f_end;
-        base[h] = (int64_t)f * p.shift - (p.snip_edges ? 0 : (p.size / 2 - p.shift / 2));
+        base[h] = (int64_t)f * p.shift + frame_offset(p.size, p.shift, p.frame_mode);
       }
       auto sample = [&](int h, int j) -> float {
         int64_t v = base[h] + j;
-        if (!p.snip_edges) v = reflect_index(v, c.n_rs);
+        if (p.frame_mode != 0) v = reflect_index(v, c.n_rs, p.frame_mode);
         return ybuf[v - s_lo];
       };
       for (int h = 0; h < 2; ++h) {
@@ -252,6 +258,7 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
     const float* P = pbuf + (size_t)f * NB + st;
     float acc = 0.f;
     for (int j = 0; j < cn; ++j) acc = fmaf(__ldg(w + j), P[j], acc);
+    if (p.db_mode) return 10.f * log10f(fmaxf(acc, 1e-10f));           // amplitude_to_DB, functional.py:390-396 (ref = 1, power)
     if (p.use_log) acc = logf(fmaxf(acc, B200_FLT_EPSILON));           // kaldi.py:633
     return acc;
   };
@@ -277,11 +284,13 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
     mk = mk_local;
   }
   const int ncell = rows * p.n_cols;
+  float vmax = -INFINITY;                      // db_mode: running maximum over this tile's real cells
   if (p.layout == 0) {
     float* o = p.out + ((size_t)b * p.out_frames + t0) * p.n_cols;
     for (int idx = tid; idx < ncell; idx += nt) {
       int f = idx / p.n_cols, col = idx - f * p.n_cols;
       float x = (f < nf) ? cell(f, col) : 0.f;
+      if (f < nf) vmax = fmaxf(vmax, x);
       o[idx] = finish_cell(p, x, t0 + f, col, mk);
     }
   } else {
@@ -289,8 +298,73 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
     for (int idx = tid; idx < ncell; idx += nt) {
       int col = idx / rows, f = idx - col * rows;
       float x = (f < nf) ? cell(f, col) : 0.f;
+      if (f < nf) vmax = fmaxf(vmax, x);
       o[(size_t)col * p.out_frames + f] = finish_cell(p, x, t0 + f, col, mk);
     }
+  }
+  if (p.db_mode && p.clip_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > -INFINITY) atomic_max_float(p.clip_max + b, vmax);
+  }
+}
+
+// AmplitudeToDB(top_db) clamp + the reference's per-clip normalisation (src/datasets/preprocessing.py:1027-1037;
+// torchaudio/functional/functional.py:398-402), in place on the dB values the main kernel wrote.  One CTA per
+// clip: clamp to (clip max - top_db) while summing in float64, then (x - mean) / unbiased_std * target_std +
+// target_mean (skipped when std == 0), SpecAugment zero-fill last.
+__global__ void melspec_finalize_kernel(const FbankParams p, float top_db, int normalize) {
+  __shared__ double red[2][32];
+  __shared__ float s_mu, s_inv;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ClipInfo c = clip_info(p, b);
+  const int m_eff = (int)(c.m < p.out_frames ? c.m : p.out_frames);
+  float* o = p.out + (size_t)b * p.out_frames * p.n_cols;
+  const size_t st_t = p.layout == 0 ? p.n_cols : 1, st_c = p.layout == 0 ? 1 : p.out_frames;
+  const float floor_db = (top_db >= 0.f && p.clip_max) ? p.clip_max[b] - top_db : -INFINITY;
+  const int ncell = m_eff * p.n_cols;
+  double s = 0.0, ss = 0.0;
+  for (int idx = tid; idx < ncell; idx += blockDim.x) {
+    const int t = p.layout == 0 ? idx / p.n_cols : idx % m_eff;
+    const int col = p.layout == 0 ? idx - t * p.n_cols : idx / m_eff;
+    float* q = o + t * st_t + col * st_c;
+    const float x = fmaxf(*q, floor_db);
+    *q = x;
+    s += (double)x; ss += (double)x * (double)x;
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, k); ss += __shfl_xor_sync(0xffffffffu, ss, k); }
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+  __syncthreads();
+  if (tid == 0) {
+    double S = 0.0, SS = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { S += red[0][w]; SS += red[1][w]; }
+    const double n = (double)ncell;
+    const double mu = n > 0 ? S / n : 0.0;
+    const double var = n > 1 ? (SS - n * mu * mu) / (n - 1.0) : 0.0;      // torch .std(): unbiased
+    const double sd = var > 0 ? sqrt(var) : 0.0;
+    s_mu = (float)mu;
+    s_inv = (normalize && sd > 0.0) ? (float)(1.0 / sd) : 0.f;
+  }
+  __syncthreads();
+  int mk_local[4];
+  const int* mk = nullptr;
+  if (p.masks) {
+    for (int i = 0; i < 4; ++i) mk_local[i] = __ldg(p.masks + (size_t)b * 4 + i);
+    mk = mk_local;
+  }
+  const bool do_norm = s_inv > 0.f;
+  if (!do_norm && !mk) return;
+  const float mu = s_mu, inv = s_inv;
+  const int nall = p.out_frames * p.n_cols;
+  for (int idx = tid; idx < nall; idx += blockDim.x) {
+    const int t = p.layout == 0 ? idx / p.n_cols : idx % p.out_frames;
+    const int col = p.layout == 0 ? idx - t * p.n_cols : idx / p.out_frames;
+    float* q = o + t * st_t + col * st_c;
+    float x = *q;
+    if (do_norm) x = (x - mu) * inv * p.target_std + p.target_mean;
+    if (mk && ((t >= mk[0] && t < mk[0] + mk[1]) || (col >= mk[2] && col < mk[2] + mk[3]))) x = 0.f;
+    *q = x;
   }
 }
 
@@ -317,6 +391,11 @@ __global__ void cms_kernel(const FbankParams p) {
       o[t * st_t + col * st_c] = finish_cell(p, x, t, col, mk);
     }
   }
+}
+
+__global__ void fill_u32_kernel(unsigned* dst, unsigned v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
 }
 
 // Resample-only kernel (resample_waveform, src/datasets/preprocessing.py:61-76).

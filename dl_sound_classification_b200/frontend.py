@@ -262,6 +262,61 @@ class FbankFrontend:
         return sums
 
 
+class MelSpecFrontend(FbankFrontend):
+    """The reference-ACTUAL recipe: ``MelSpectrogram(sample_rate, n_fft, hop_length,
+    win_length, n_mels, power=2)`` + ``AmplitudeToDB(top_db)`` + the per-clip normalisation of
+    ``ASTPreprocessor.preprocess`` (src/datasets/preprocessing.py:988-998, 1013-1039; src/utils/audio.py:60-84),
+    batched on the GPU.  Features are computed at ``sample_rate``; clips at another rate of ``orig_rates`` are
+    resampled first (``resample_waveform``, :61-76)."""
+
+    def __init__(self, sample_rate: int = 44100, n_fft: int = 1024, hop_length: int = 160,
+                 win_length: Optional[int] = 400, n_mels: int = 128, top_db: Optional[float] = 80.0,
+                 orig_rates: Optional[Sequence[int]] = None, device=None, host_only: bool = False):
+        self.orig_rates = tuple(int(r) for r in (orig_rates or (sample_rate,)))
+        self.kaldi = {}
+        opts = make_opts(self.orig_rates, sample_frequency=float(sample_rate), num_mel_bins=int(n_mels),
+                         low_freq=0.0, high_freq=0.0)
+        opts.frontend = K.FRONTEND_MELSPEC_DB
+        opts.n_fft, opts.hop_length = int(n_fft), int(hop_length)
+        opts.win_length = int(win_length) if win_length else int(n_fft)
+        opts.top_db = float(top_db) if top_db is not None else -1.0
+        self.sample_rate, self.top_db = int(sample_rate), top_db
+        if host_only:
+            self.device = None
+            self.plan = K.Plan(opts, -1)
+        else:
+            self.device = _require_cuda(device)
+            self.plan = K.Plan(opts, self.device.index)
+        self.n_cols = self.plan.n_cols
+        with _plans_lock:
+            self.plan_id = (max(_plans) + 1) if _plans else 1
+            _plans[self.plan_id] = self
+
+    def __call__(self, wav: torch.Tensor, out_frames: int, offsets: Optional[torch.Tensor] = None,
+                 rate_ids: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None, to_db: bool = True,
+                 normalize: bool = True, target_mean: float = 0.0, target_std: float = 0.5, layout: str = "bft",
+                 out: Optional[torch.Tensor] = None, return_n_frames: bool = True):
+        wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
+        lay = {"btf": K.LAYOUT_BTF, "bft": K.LAYOUT_BFT}[layout]
+        shape = (B, int(out_frames), self.n_cols) if lay == K.LAYOUT_BTF else (B, 1, self.n_cols, int(out_frames))
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 {shape} tensor on {self.device}")
+        nfr = torch.empty(B, dtype=torch.int32, device=self.device) if return_n_frames else None
+        mk = self._dev(masks, torch.int32, "masks")
+        if mk is not None and tuple(mk.shape) != (B, 4):
+            raise ValueError("masks must be (B, 4) int32: t_start, t_len, f_start, f_len")
+        cmax = torch.empty(max(B, 1), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            K.check(K.lib.b200fbank_melspec_db(
+                self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B, self._ptr(mk),
+                int(bool(to_db)), int(bool(normalize)), float(target_mean), float(target_std), int(out_frames), lay,
+                out.data_ptr(), self._ptr(nfr), cmax.data_ptr(), stream))
+        return out, nfr
+
+
 def launch_count(reset: bool = False) -> int:
     """Kernel launches issued by this thread through the C ABI (bench.py ``gpu_launches``)."""
     return int(K.lib.b200fbank_launch_count(1 if reset else 0))

@@ -26,7 +26,7 @@ from typing import Any, Dict, List, Optional, Sequence
 import torch
 
 from . import specaugment as _sa
-from .frontend import AST_FBANK_KWARGS, FbankFrontend, _require_cuda
+from .frontend import AST_FBANK_KWARGS, FbankFrontend, MelSpecFrontend, _require_cuda
 
 logger = logging.getLogger(__name__)
 
@@ -169,9 +169,6 @@ class ASTPreprocessor(BasePreprocessor):
             raise ValueError("norm_mean and norm_std must be given together")
         if self.frontend_name not in ("kaldi_fbank", "melspectrogram"):
             raise ValueError(f"Unknown frontend: {self.frontend_name}")
-        if self.frontend_name == "melspectrogram":
-            raise NotImplementedError("frontend='melspectrogram' (the reference's MelSpectrogram+AmplitudeToDB recipe, "
-                                      "SURVEY.md section 8f N1) is not built yet; use frontend='kaldi_fbank'")
         self.n_fft, self.hop_length, self.win_length = AST_N_FFT, AST_HOP_LENGTH, AST_WIN_LENGTH
         rates = [int(self.sample_rate)] + [int(r) for r in c.get("extra_rates", ())]
         self.rates = tuple(dict.fromkeys(rates))
@@ -186,7 +183,12 @@ class ASTPreprocessor(BasePreprocessor):
     @property
     def frontend(self) -> FbankFrontend:
         if self._fe is None:
-            self._fe = FbankFrontend(orig_rates=self.rates, device=_require_cuda(self._device), **self._kw)
+            if self.frontend_name == "melspectrogram":      # the reference's own recipe, computed at self.sample_rate
+                self._fe = MelSpecFrontend(int(self.sample_rate), self.n_fft, self.hop_length, self.win_length,
+                                           int(self.n_mels), 80.0, orig_rates=self.rates,
+                                           device=_require_cuda(self._device))
+            else:
+                self._fe = FbankFrontend(orig_rates=self.rates, device=_require_cuda(self._device), **self._kw)
         return self._fe
 
     def get_cache_suffix(self) -> str:
@@ -221,6 +223,11 @@ class ASTPreprocessor(BasePreprocessor):
             T = max(fe.num_frames(n, r) for n, r in zip(max_len, rids))
             if T <= 0:
                 raise AssertionError("choose a window size {} that is [2, {}]".format(fe.plan.window_size, min(max_len)))
+        if self.frontend_name == "melspectrogram":
+            # src/datasets/preprocessing.py:1024-1037: dB, top_db clamp and per-clip normalisation are fused passes
+            return fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids, masks=masks, to_db=True,
+                      normalize=bool(self.normalize), target_mean=self.target_mean, target_std=self.target_std,
+                      layout="bft")
         mean = std = None
         if self.normalize and self.norm_mean is not None:
             mean, std = self.norm_mean, self.norm_std
@@ -285,6 +292,30 @@ class ASTPreprocessor(BasePreprocessor):
 
 
 B200ASTPreprocessor = ASTPreprocessor
+
+
+@lru_cache(maxsize=16)
+def _melspec_frontend(device_index: int, sr: int, n_mels: int, n_fft: int, hop_length: int) -> MelSpecFrontend:
+    return MelSpecFrontend(sr, n_fft, hop_length, None, n_mels, 80.0, device=torch.device("cuda", device_index))
+
+
+def melspectrogram(wav: torch.Tensor, sr: int = 44100, n_mels: int = 128, n_fft: int = 1_024, hop_length: int = 512,
+                   log_scale: bool = True) -> torch.Tensor:
+    """Mirror of src/utils/audio.py:60-84: waveform ``(1, N)`` -> ``(1, n_mels, frames)`` (dB, top_db=80, if
+    ``log_scale``) via ``MelSpectrogram(win_length=n_fft, center=True)`` -- the fallback frontend of
+    ``create_ast_fallback_spectrogram`` (src/datasets/preprocessing.py:79-97)."""
+    dev = _require_cuda(wav.device if wav.is_cuda else None)
+    fe = _melspec_frontend(dev.index, int(sr), int(n_mels), int(n_fft), int(hop_length))
+    w = wav.reshape(-1, wav.shape[-1])[:1].to(torch.float32)
+    T = fe.num_frames(int(w.shape[-1]))
+    out, _ = fe(w, out_frames=T, to_db=bool(log_scale), normalize=False, layout="bft", return_n_frames=False)
+    out = out[0]
+    return out if out.device == wav.device else out.to(wav.device)
+
+
+def create_ast_fallback_spectrogram(waveform: torch.Tensor, sample_rate: int, n_mels: int = 128) -> torch.Tensor:
+    """src/datasets/preprocessing.py:79-97."""
+    return melspectrogram(waveform, sample_rate, n_mels, AST_N_FFT, AST_HOP_LENGTH, log_scale=True)
 
 
 class PreprocessingCache:

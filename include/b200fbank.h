@@ -167,6 +167,20 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
                       float target_mean, float target_std, int out_frames, int layout,
                       float* d_out, int32_t* d_n_frames, void* stream);
 
+/*
+ * The reference-ACTUAL recipe on a MELSPEC_DB plan: resample-if-needed ->
+ * MelSpectrogram(n_fft, win_length, hop_length, power=2, center, reflect, periodic Hann, HTK mel, norm=None)
+ * -> AmplitudeToDB(top_db) -> per-clip (x - mean) / unbiased_std * target_std + target_mean.  Replaces
+ * ASTPreprocessor.preprocess (src/datasets/preprocessing.py:1013-1039) and melspectrogram()
+ * (src/utils/audio.py:60-84).  to_db = 0 returns the raw mel power (log_scale=False); normalize = 0 skips
+ * the per-clip normalisation.  d_clip_max: [B] floats of workspace (receives each clip's dB maximum).
+ * Output rows past a clip's frame count (1 + n/hop) hold 0.0.
+ */
+int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                         int64_t clip_samples, const int32_t* d_rate_id, int B, const int32_t* d_masks,
+                         int to_db, int normalize, float target_mean, float target_std, int out_frames,
+                         int layout, float* d_out, int32_t* d_n_frames, float* d_clip_max, void* stream);
+
 /* Dataset-statistics pass (north_star config 4; no reference code): the same fused path
    with the epilogue replaced by float64 accumulation of per-column sum / sum of squares
    over the REAL frames [0, min(frames, max_frames)) of every clip.  d_sums is

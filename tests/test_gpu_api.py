@@ -215,3 +215,52 @@ def test_config4_stats_sharded_partials_add_up(b2, O):
     assert (np.abs(sub.mean_per_bin.numpy() - rm) <= 1e-4 * (np.abs(rm) + rs)).all()
     keep = np.arange(128) != 3
     np.testing.assert_allclose(sub.std_per_bin.numpy()[keep], rs[keep], rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# N1: the reference-actual recipe (MelSpectrogram + AmplitudeToDB + per-clip normalisation)
+# ---------------------------------------------------------------------------------------------
+def test_reference_actual_frontend_vs_golden(b2, O, golden):
+    g = golden("reference_actual.npz")
+    w = short_clip(44100, seed=77)
+    cfg = dict(sample_rate=44100, n_mels=128, bc_mixing=False, normalize=True, target_mean=0.0, target_std=0.5,
+               frontend="melspectrogram")
+    pre = b2.create_preprocessor("ast", cfg, "/tmp/unused")
+    a = pre.preprocess(w, 44100)
+    assert a.device.type == "cpu" and tuple(a.shape) == (1, 128, 276)
+    assert np.abs(a.numpy() - g["ast_44k"]).max() < 5e-4              # output of the reference's own ASTPreprocessor
+    assert abs(float(a.mean())) < 1e-4 and abs(float(a.std()) - 0.5) < 1e-4
+    w2 = short_clip(22050, seed=78)                                    # 22.05 kHz clip: resampled to 44.1 kHz first
+    pre2 = b2.create_preprocessor("ast", dict(cfg, extra_rates=[22050]), "/tmp/unused")
+    b = pre2.preprocess(w2, 22050)
+    assert np.abs(b.numpy() - g["ast_22k"]).max() < 5e-4
+    nn = b2.create_preprocessor("ast", dict(cfg, normalize=False), "/tmp/unused").preprocess(w, 44100)
+    assert np.abs(nn.numpy() - g["ast_44k_nonorm"]).max() < 5e-3      # dB units
+    assert float(nn.max() - nn.min()) <= 80.0 + 1e-3                   # top_db clamp
+    fb = b2.melspectrogram(w, 44100, 128, 1024, 160, log_scale=True)   # fallback frontend, win_length = n_fft
+    assert tuple(fb.shape) == (1, 128, 276) and np.abs(fb.numpy() - g["fallback_melspec"]).max() < 5e-3
+    ref = O.reference_ast_preprocess(w.numpy(), 44100)
+    assert np.abs(a.numpy() - ref).max() < 5e-4
+
+
+def test_reference_actual_batch_and_masks(b2, O):
+    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, frontend="melspectrogram"))
+    clips = config1_clips(3, length=66150)
+    random.seed(9)
+    masks = pre.draw_specaugment_masks(3, 414, 192, 48)
+    out, nfr = pre.preprocess_batch(torch.cat(clips, 0), 44100, masks=masks)
+    assert tuple(out.shape) == (3, 1, 128, 414) and nfr.cpu().tolist() == [414] * 3
+    random.seed(9)
+    for i, c in enumerate(clips):
+        want = pre.apply_specaugment(pre.preprocess(c, 44100), 192, 48)
+        assert torch.equal(out[i].cpu(), want), i
+        ref = O.reference_ast_preprocess(c.numpy(), 44100)
+        ref = O.apply_mask_intervals(ref, masks[i].tolist(), layout="ft")
+        assert np.abs(out[i].cpu().numpy() - ref).max() < 5e-4
+    live = pytest.importorskip("torchaudio")
+    import torchaudio.transforms as T
+    w = clips[0]
+    db = T.AmplitudeToDB(top_db=80)(T.MelSpectrogram(44100, n_fft=1024, hop_length=160, win_length=400, n_mels=128, power=2.0)(w))
+    mine = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, frontend="melspectrogram",
+                                                     normalize=False)).preprocess(w, 44100)
+    assert np.abs(mine.numpy() - db.numpy()).max() < 5e-3
