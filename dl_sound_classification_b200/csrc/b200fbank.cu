@@ -405,8 +405,8 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     f.gen_part[ri] = part;
   }
   p->fast_smem = (size_t)(FK_ATFLOATS + FK_RING_FLOATS + 1024 + rows * 32) * 4;
-  // the AST-specialised variants: (2,3,6,11)-tap mel groups, power spectrum, log output
-  f.ast_bank = (f.mel_groups == 4 && f.mel_maxcnt[0] == 2 && f.mel_maxcnt[1] == 3 && f.mel_maxcnt[2] == 6 && f.mel_maxcnt[3] == 11 &&
+  // the AST-specialised variants: (2,3,6,10)-tap mel groups, power spectrum, log output
+  f.ast_bank = (f.mel_groups == 4 && f.mel_maxcnt[0] == 2 && f.mel_maxcnt[1] == 3 && f.mel_maxcnt[2] == 6 && f.mel_maxcnt[3] == 10 &&
                 o.use_power && o.use_log_fbank);
   if (p->fast_smem > 113 * 1024) return 0;
   auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {

@@ -56,7 +56,7 @@ struct FastParams {
   int mel_rows;           // sum of mel_maxcnt
   int gen_part[B200_MAX_RATES];   // outputs per staging pass for rates on the per-sample path
   int seg_frames, segs;
-  int ast_bank;           // 1: filter lengths per group are (2,3,6,11) -> fully unrolled mel
+  int ast_bank;           // 1: filter lengths per group are (2,3,6,10) -> fully unrolled mel
   // warp-specialised kernel (fbank_ws.cuh): register-resident taps, phase r of group g starts at dense
   // index ws_k0g[g] + {0,2,4,6,10}[r] and keeps 36 taps (even offsets keep input pairs aligned for FFMA2)
   const float* ws_taps;   // [32][5][36]
@@ -259,7 +259,7 @@ __device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, cons
 // One frame pass of a warp: four consecutive frames starting at output row t0, whose samples start at
 // `rows` (ring rows of stride RS; 6 rows are touched) -> 4 x n_mel outputs.  n_live = how many of the four are
 // real frames (the rest are pad rows).  Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths
-// (2,3,6,11) of the AST bank.
+// (2,3,6,10) of the AST bank.
 template <bool STATS, bool AST, int RS, class LC>
 __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const LC& L,
                                               const float* __restrict__ rows, float* __restrict__ Ebuf,
@@ -325,7 +325,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         if (i == 0) fk_mel_group<2>(P4, wrow, L.ms(i), 0, acc);
         else if (i == 1) fk_mel_group<3>(P4, wrow, L.ms(i), 0, acc);
         else if (i == 2) fk_mel_group<6>(P4, wrow, L.ms(i), 0, acc);
-        else fk_mel_group<11>(P4, wrow, L.ms(i), 0, acc);
+        else fk_mel_group<10>(P4, wrow, L.ms(i), 0, acc);
       } else {
         fk_mel_group<-1>(P4, wrow, L.ms(i), fp.mel_maxcnt[i], acc);
       }
