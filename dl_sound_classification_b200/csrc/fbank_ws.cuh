@@ -182,23 +182,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
     mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
   }
-  if (tid < 32) {                                                 // lane constants: one copy per CTA (= per clip)
-    for (int j = 0; j < 13; ++j) slane[j * 32 + lane] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
-    for (int i = 0; i < 4; ++i) {
-      const int m = lane + 32 * i;
-      float mean = 0.f, scale = 1.f, shift = 0.f;
-      if (!STATS && p.n_stats > 0 && m < p.n_mel) {
-        const int si = p.n_stats == 1 ? 0 : m;
-        mean = __ldg(p.mean + si);
-        scale = p.target_std / __ldg(p.std + si);
-        shift = p.target_mean;
-      }
-      if (m >= mk2 && m < mk2 + mk3) { scale = 0.f; shift = 0.f; }     // frequency mask: the whole column is 0.0
-      slane[(13 + i) * 32 + lane] = __int_as_float((m < p.n_mel) ? __ldg(p.mel_start + m) : 0);
-      slane[(17 + i) * 32 + lane] = mean;
-      slane[(21 + i) * 32 + lane] = scale;
-      slane[(25 + i) * 32 + lane] = shift;
+  // lane constants: one copy per CTA (= per clip); 29 rows x 32 lanes spread over all threads so the dependent
+  // global loads of the set-up overlap
+  for (int e = tid; e < FK_LANE_ROWS * 32; e += WS_THREADS) {
+    const int row = e >> 5, ln = e & 31;
+    float v;
+    if (row < 13) {
+      v = (ln + 32 * row < FK_SIZE) ? __ldg(p.window + ln + 32 * row) : 0.f;
+    } else {
+      const int i = (row - 13) & 3, kind = (row - 13) >> 2;      // kind 0 mstart, 1 mean, 2 scale, 3 shift
+      const int m = ln + 32 * i;
+      const bool fmask = (m >= mk2 && m < mk2 + mk3);            // frequency mask: the whole column is 0.0
+      const bool norm = !STATS && p.n_stats > 0 && m < p.n_mel;
+      const int si = p.n_stats == 1 ? 0 : m;
+      if (kind == 0) v = __int_as_float((m < p.n_mel) ? __ldg(p.mel_start + m) : 0);
+      else if (kind == 1) v = norm ? __ldg(p.mean + si) : 0.f;
+      else if (kind == 2) v = fmask ? 0.f : (norm ? p.target_std / __ldg(p.std + si) : 1.f);
+      else v = (fmask || !norm) ? 0.f : p.target_mean;
     }
+    slane[e] = v;
   }
   __syncthreads();
 
