@@ -38,6 +38,20 @@ UNIT = "audio-s/s"
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ws_full_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_ws_full_metrics.csv")):
+            f = line.strip().split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -128,7 +142,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -289,7 +303,7 @@ def run_b200(args, rank, local_rank, world):
                         l2=f"inputs {B * CLIP_SAMPLES * 4 / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)",
                         kernel=os.environ.get("B200FBANK_KERNEL", "auto")),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
+                          traffic=measured_traffic() if B == 1024 else None, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                           kernel_ms=k_ms),
             cpu_baseline=cpu,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * CLIP_SAMPLES * 4,
@@ -303,8 +317,8 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
