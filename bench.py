@@ -314,6 +314,116 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_extra(args, rank, local_rank, world):
+    """Secondary BASELINE.json configs (documentation runs, not the driver's headline line):
+    us8k  = configs[2]: 4096 ragged <=4 s clips at 22.05/44.1/48 kHz -> 1024 frames, SpecAugment masks;
+    stats = configs[3]: per-bin sum / sum-of-squares over --clips synthetic clips sharded over the ranks + one
+            all-reduce of 257 doubles;
+    sweep = configs[4]: batch 64 .. 65536 clips (chunked at 4096 clips per launch)."""
+    import random as _random
+    import torch
+    import torch.distributed as dist
+    import dl_sound_classification_b200 as b2
+    from dl_sound_classification_b200 import stats as ST
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup=3):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    out_lines = []
+    if args.workload == "us8k":
+        B, table = 4096, (22050, 44100, 48000)
+        g = torch.Generator().manual_seed(31 + rank)
+        rid = torch.randint(0, 3, (B,), generator=g)
+        lens = ((1.0 + 3.0 * torch.rand(B, generator=g)) * torch.tensor(table)[rid]).long()
+        offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)]).to(dev)
+        flat = torch.rand(int(offsets[-1]), generator=gen, device=dev) * 2 - 1
+        fe = b2.FbankFrontend(orig_rates=table, device=dev, **b2.AST_FBANK_KWARGS)
+        _random.seed(77)
+        masks = b2.specaugment.draw_masks(B, 1024, 128, 192, 48).to(dev)
+        rid_d = rid.int().to(dev)
+        out = torch.empty((B, 1024, N_MELS), device=dev)
+        mean, std = torch.tensor([AST_MEAN], device=dev), torch.tensor([AST_STD], device=dev)
+        ms = timed(lambda: fe(flat, 1024, offsets=offsets, rate_ids=rid_d, masks=masks, mean=mean, std=std, out=out,
+                              return_n_frames=False), args.steps)
+        secs = float((lens.double() / torch.tensor(table, dtype=torch.float64)[rid]).sum())
+        alg = int(lens.sum()) * 4 + B * 1024 * N_MELS * 4
+        out_lines.append(dict(workload="us8k: 4096 ragged clips (1-4 s @22.05/44.1/48 kHz) -> 1024 frames + SpecAugment masks",
+                              ms_per_step=ms, value=world * secs / (ms * 1e-3), unit=UNIT,
+                              roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], audio_seconds_per_step=secs))
+    elif args.workload == "stats":
+        total = args.clips
+        lo, hi = ST.shard_bounds(total, rank, world)
+        chunk = 4096
+        fe = b2.FbankFrontend(orig_rates=(44100,), device=dev, **b2.AST_FBANK_KWARGS)
+        ds = b2.DatasetStats(fe, OUT_FRAMES)
+        wav = torch.empty((chunk, CLIP_SAMPLES), device=dev)
+        ev = []
+        barrier()
+        for c0 in range(lo, hi, chunk):
+            n = min(chunk, hi - c0)
+            wav[:n].uniform_(-1, 1, generator=gen)                  # synthetic clips generated on the device (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ds.update(wav[:n]); e1.record()
+            ev.append((e0, e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ds.all_reduce(); e1.record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev), e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st = ds.finalize()
+        ms = float(t[0]) + float(t[1])
+        out_lines.append(dict(workload=f"stats: {total} synthetic ESC-50 clips sharded over {world} GPU(s), per-bin sum/sumsq + all-reduce",
+                              ms_total=ms, ms_allreduce=float(t[1]), value=total * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                              frames=st.frames, mean=st.mean, std=st.std,
+                              roofline_frac=(total / world) * CLIP_SAMPLES * 4 / (float(t[0]) * 1e-3) / 1e9 / measured_peaks()[0]))
+    elif args.workload == "sweep":
+        fe = b2.FbankFrontend(orig_rates=(44100,), device=dev, **b2.AST_FBANK_KWARGS)
+        mean, std = torch.tensor([AST_MEAN], device=dev), torch.tensor([AST_STD], device=dev)
+        for B in (64, 256, 1024, 4096, 16384, 65536):
+            nb = min(B, 4096)
+            wav = torch.rand((nb, CLIP_SAMPLES), generator=gen, device=dev) * 2 - 1
+            out = torch.empty((nb, OUT_FRAMES, N_MELS), device=dev)
+            reps = B // nb
+
+            def step():
+                for _ in range(reps):                                  # > 4096 clips: streamed in 4096-clip launches
+                    fe(wav, OUT_FRAMES, mean=mean, std=std, out=out, return_n_frames=False)
+            ms = timed(step, max(3, args.steps // max(1, reps)))
+            out_lines.append(dict(workload=f"sweep: batch {B} per GPU", ms_per_step=ms,
+                                  value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                                  roofline_frac=B * (CLIP_SAMPLES * 4 + OUT_FRAMES * N_MELS * 4) / (ms * 1e-3) / 1e9 / measured_peaks()[0]))
+            del wav, out
+    if rank == 0:
+        for d in out_lines:
+            print(json.dumps(dict(metric=METRIC, n_gpus=world, dtype="f32", data="synthetic", **d)), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,6 +432,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep"],
+                    help="esc50 = the headline line (BASELINE.json configs[1]); the others are documentation runs")
+    ap.add_argument("--clips", type=int, default=100000, help="clips of the stats workload")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per pipelined chunk of the host-in/host-out path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -329,6 +442,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload != "esc50":
+        run_extra(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 
