@@ -6,7 +6,9 @@
 // path exists: device calls on a host-only plan fail with B200FBANK_ERR_NO_DEVICE.
 #include "../../include/b200fbank.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -319,6 +321,79 @@ void generic_smem_layout(const b200fbank_plan* p, int F, int* sy, int* sx, int* 
 
 // Tables of the fast kernel (fbank_fast.cuh); leaves p->fast_ok = false when the
 // configuration is outside its envelope (the generic kernel then serves every call).
+// Wavefronts of one LDS.128 by a quarter-warp whose lanes read power cells a[0..7] (16 B each, -1 = idle lane):
+// cells in the same 16-B bank group (index mod 8) serialise unless they are the same cell.
+static int quarter_wavefronts(const int* a) {
+  int worst = 1;
+  for (int r = 0; r < 8; ++r) {
+    int seen[8], n = 0;
+    for (int l = 0; l < 8; ++l) {
+      if (a[l] < 0 || (a[l] & 7) != r) continue;
+      bool dup = false;
+      for (int q = 0; q < n; ++q) dup |= seen[q] == a[l];
+      if (!dup) seen[n++] = a[l];
+    }
+    worst = std::max(worst, n);
+  }
+  return worst;
+}
+
+// Lane slots of mel group `gi` (bins 32 gi .. 32 gi + 31): a deterministic annealing over (bin permutation, early
+// start of short filters) that minimises the LDS.128 wavefronts of the group's tap loop; identity if nothing better.
+static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin, int* start) {
+  int slack[32], sh[32], cell[32];
+  for (int l = 0; l < 32; ++l) {
+    const int m = 32 * gi + l;
+    bin[l] = m;
+    sh[l] = 0;
+    slack[l] = m < p->n_mel ? std::min(maxcnt - p->mel_cnt[m], p->mel_start[m]) : 0;
+  }
+  auto cost = [&]() {
+    int c = 0;
+    for (int q = 0; q < 4; ++q) {
+      for (int l = 0; l < 8; ++l) {
+        const int m = bin[8 * q + l];
+        cell[l] = m < p->n_mel ? p->mel_start[m] - sh[m - 32 * gi] : -1;
+      }
+      c += quarter_wavefronts(cell);
+    }
+    return c;
+  };
+  uint64_t rng = 0x9E3779B97F4A7C15ull + (uint64_t)gi;
+  auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+  int cur = cost(), best = cur, best_bin[32], best_sh[32];
+  std::copy(bin, bin + 32, best_bin); std::copy(sh, sh + 32, best_sh);
+  double T = 1.0;
+  for (int it = 0; it < 60000 && best > 4; ++it, T = std::max(0.05, T * 0.9999)) {
+    const int a = (int)(next() & 31), b = (int)(next() & 31);
+    const bool swap_move = (next() & 1) != 0;
+    int old_sh = 0;
+    if (swap_move) {
+      if ((a >> 3) == (b >> 3)) continue;
+      std::swap(bin[a], bin[b]);
+    } else {
+      if (slack[a] == 0) continue;
+      old_sh = sh[a];
+      sh[a] = (int)(next() % (uint32_t)(slack[a] + 1));
+    }
+    const int c2 = cost();
+    const double u = (double)(next() & 0xFFFFFF) / (double)0x1000000;
+    if (c2 <= cur || u < std::exp((double)(cur - c2) / T)) {
+      cur = c2;
+      if (cur < best) { best = cur; std::copy(bin, bin + 32, best_bin); std::copy(sh, sh + 32, best_sh); }
+    } else if (swap_move) {
+      std::swap(bin[a], bin[b]);
+    } else {
+      sh[a] = old_sh;
+    }
+  }
+  for (int l = 0; l < 32; ++l) {
+    bin[l] = best_bin[l];
+    const int m = bin[l];
+    start[l] = m < p->n_mel ? p->mel_start[m] - best_sh[m - 32 * gi] : 0;
+  }
+}
+
 int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   using namespace b200;
   const b200fbank_opts& o = p->o;
@@ -384,15 +459,21 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     f.mel_maxcnt[i] = mc; f.mel_woff[i] = rows; rows += mc;
   }
   f.mel_rows = rows;
+  // Lane slots: inside each group of 32 bins, permute the bins over the lanes and let short filters start up to
+  // (group length - own length) FFT bins early (zero leading weights) so that the 8 lanes of every quarter-warp
+  // read 8 different 16-B bank groups of the 4-frame power cells (or the very same cell): LDS.128 conflict free.
+  std::vector<int> slot_bin(32 * f.mel_groups), slot_start(32 * f.mel_groups, 0);
+  for (int i = 0; i < f.mel_groups; ++i) plan_mel_slots(p, i, f.mel_maxcnt[i], slot_bin.data() + 32 * i, slot_start.data() + 32 * i);
   std::vector<float> melw((size_t)std::max(rows, 1) * 32, 0.f);
   for (int i = 0; i < f.mel_groups; ++i)
-    for (int j = 0; j < f.mel_maxcnt[i]; ++j)
-      for (int l = 0; l < 32; ++l) {
-        const int m = 32 * i + l;
-        // the kernel leaves out the 1/4 (power) or 1/2 (magnitude) of the conjugate split: exact power-of-two fold
-        if (m < p->n_mel && j < p->mel_cnt[m])
-          melw[(size_t)(f.mel_woff[i] + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * (o.use_power ? 0.25f : 0.5f);
-      }
+    for (int l = 0; l < 32; ++l) {
+      const int m = slot_bin[32 * i + l];
+      if (m >= p->n_mel) continue;
+      const int lead = p->mel_start[m] - slot_start[32 * i + l];
+      // the kernel leaves out the 1/4 (power) or 1/2 (magnitude) of the conjugate split: exact power-of-two fold
+      for (int j = 0; j < p->mel_cnt[m]; ++j)
+        melw[(size_t)(f.mel_woff[i] + lead + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * (o.use_power ? 0.25f : 0.5f);
+    }
   for (size_t ri = 0; ri < p->rates.size(); ++ri) {
     const RateHost& r = p->rates[ri];
     int part = FK_RING_HOPS * FK_SHIFT;
@@ -421,6 +502,8 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   if (int rc = dev_copy(k0g.data(), k0g.size() * 4, (const void**)&f.k0g)) return rc;
   if (int rc = dev_copy(tw.data(), tw.size() * 4, (const void**)&f.tw)) return rc;
   if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
+  if (int rc = dev_copy(slot_bin.data(), slot_bin.size() * 4, (const void**)&f.mel_slot_bin)) return rc;
+  if (int rc = dev_copy(slot_start.data(), slot_start.size() * 4, (const void**)&f.mel_slot_start)) return rc;
   // ---- warp-specialised kernel: register-resident taps [32][5][36], even phase offsets ----------
   {
     std::vector<float> wt((size_t)FK_NG * WS_GROUP_FLOATS, 0.f);

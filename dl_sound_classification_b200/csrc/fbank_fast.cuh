@@ -34,7 +34,8 @@ constexpr int FK_RING_STRIDE = 161;       // hop stride in the ring: odd -> conf
 constexpr int FK_RING_HOPS = 34;
 constexpr int FK_RING_FLOATS = 5476;      // 34 * 161 = 5474, padded to a multiple of 4
 constexpr int FK_EROW = 33;               // float2 per exchange row (32 + 1 pad: conflict-free, no index math)
-constexpr int FK_EBUF = 2 * 16 * FK_EROW * 2;   // floats per warp: two 16 x 33 complex exchange buffers; later 256 x 4 powers
+constexpr int FK_EB_SKEW = 8;             // float2 between the two exchange buffers: rows of transform B sit 8 bank pairs from transform A's
+constexpr int FK_EBUF = 2 * 16 * FK_EROW * 2 + 2 * FK_EB_SKEW;   // floats per warp: two 16 x 33 complex exchange buffers; later 256 x 4 powers
 constexpr int FK_XFLOATS = 15040;         // 33 * 441 + 475 + slack, multiple of 4
 constexpr int FK_TAPFLOATS = FK_NG * FK_GROUP_FLOATS;   // 5632
 // Region AT = [x chunk | taps]; the FFT phase reuses its front as 8 x FK_EBUF exchange buffers, so the
@@ -54,6 +55,11 @@ struct FastParams {
   int mel_maxcnt[4];      // longest filter in each group of 32 bins
   int mel_woff[4];        // row offset of each group in melw
   int mel_rows;           // sum of mel_maxcnt
+  // lane slot (group i, lane l) owns mel bin mel_slot_bin[32 i + l] (a permutation inside each group of 32 bins) and
+  // starts its taps at FFT bin mel_slot_start[32 i + l] (<= the filter's first bin; leading weights are zero):
+  // chosen on the host so the 8 lanes of every quarter-warp read 8 different 16-B bank groups (LDS.128 conflict free)
+  const int* mel_slot_bin;
+  const int* mel_slot_start;
   int gen_part[B200_MAX_RATES];   // outputs per staging pass for rates on the per-sample path
   int seg_frames, segs;
   int ast_bank;           // 1: filter lengths per group are (2,3,6,10) -> fully unrolled mel
@@ -166,22 +172,36 @@ __device__ __forceinline__ int fk_load_x_async(const float* g /* = clip + in_lo 
 // Per-lane constants of the frame pass (live for the whole kernel).
 struct FkLane {
   float win[13];        // window at n = lane + 32 j
-  int mstart[4];        // first FFT bin of mel filters lane + 32 i
-  float nmean[4], nscale[4], nshift[4];   // epilogue: (x - nmean) * nscale + nshift (frequency mask folded in)
+  int mstart[4];        // first FFT bin read by lane slot (i, lane)
+  int mbin[4];          // mel bin of lane slot (i, lane); >= n_mel: no bin
+  float nscale[4], nshift[4];   // epilogue: y = v * nscale + nshift, v = lg2(mel) (log output) or mel; see fk_fold_norm
   __device__ __forceinline__ float w(int j) const { return win[j]; }
   __device__ __forceinline__ int ms(int i) const { return mstart[i]; }
-  __device__ __forceinline__ float mean(int i) const { return nmean[i]; }
+  __device__ __forceinline__ int bin(int i) const { return mbin[i]; }
   __device__ __forceinline__ float scale(int i) const { return nscale[i]; }
   __device__ __forceinline__ float shift(int i) const { return nshift[i]; }
 };
 
+// Epilogue constants of mel bin m: normalisation (x - mean) * (target_std / std) + target_mean folded with the ln 2 of
+// the lg2-based log into ONE fma per output: y = lg2(mel) * (ln2 * s) + fma(-mean, s, target_mean).  Without
+// normalisation this is lg2 * ln2 exactly as before; a frequency-masked bin has scale = shift = 0 (the column is 0.0).
+__device__ __forceinline__ void fk_fold_norm(const FbankParams& p, bool stats, bool log_out, int m, bool fmask,
+                                             float& scale, float& shift) {
+  const bool norm = !stats && p.n_stats > 0 && m < p.n_mel;
+  const int si = p.n_stats == 1 ? 0 : m;
+  const float s = norm ? p.target_std / __ldg(p.std + si) : 1.f;
+  const float k = log_out ? 0.69314718055994531f : 1.f;
+  scale = fmask ? 0.f : (norm ? k * s : k);
+  shift = (fmask || !norm) ? 0.f : fmaf(-__ldg(p.mean + si), s, p.target_mean);
+}
+
 // The same constants kept in shared memory ([row][32 lanes], one copy per CTA) and re-read at each use: frees 29
 // registers per thread for the FFT's instruction-level parallelism at the price of ~70 LDS per pass.
 struct FkLaneSm {
-  const float* base;    // rows: 0..12 window, 13..16 mstart (as int bits), 17..20 mean, 21..24 scale, 25..28 shift; + lane
+  const float* base;    // rows: 0..12 window, 13..16 mstart (as int bits), 17..20 mbin (int bits), 21..24 scale, 25..28 shift; + lane
   __device__ __forceinline__ float w(int j) const { return base[j * 32]; }
   __device__ __forceinline__ int ms(int i) const { return __float_as_int(base[(13 + i) * 32]); }
-  __device__ __forceinline__ float mean(int i) const { return base[(17 + i) * 32]; }
+  __device__ __forceinline__ int bin(int i) const { return __float_as_int(base[(17 + i) * 32]); }
   __device__ __forceinline__ float scale(int i) const { return base[(21 + i) * 32]; }
   __device__ __forceinline__ float shift(int i) const { return base[(25 + i) * 32]; }
 };
@@ -267,7 +287,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
                                               int b, int t0, int n_live, int row_end, int lane,
                                               int mk0, int mk1, int mk2, int mk3, double (&st_s)[4], double (&st_ss)[4]) {
   float2* EA = reinterpret_cast<float2*>(Ebuf);
-  float2* EB = EA + 16 * FK_EROW;
+  float2* EB = EA + 16 * FK_EROW + FK_EB_SKEW;
   constexpr int f0 = 0;
   const int nf = n_live;
   (void)mk2; (void)mk3;
@@ -282,19 +302,21 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       fk_stage1_store(z, stw, lane, tr == 0 ? EA : EB);
     }
     __syncwarp();
-    // ---- stage 2: lane = k1 + 16 * transform gathers its row, 32-point DFT over n2   // [phase: exchange]
-    const int k1l = lane & 15;
+    // ---- stage 2: lane = 2 k1 + transform gathers its row, 32-point DFT over n2   // [phase: exchange]
+    // (transform in the LOW lane bit: a half-warp then reads 8 rows of A and 8 of B, 16 distinct bank pairs thanks to
+    // FK_EB_SKEW, and later writes the 4-frame power cells of 8 consecutive bins = 128 contiguous bytes)
+    const int k1l = lane >> 1, trl = lane & 1;
     float2 u[32];
     {
-      const float2* row = (lane < 16 ? EA : EB) + k1l * FK_EROW;
+      const float2* row = (trl ? EB : EA) + k1l * FK_EROW;
 #pragma unroll
       for (int n2 = 0; n2 < 32; ++n2) u[n2] = row[n2];
     }
     __syncwarp();
     fft_dif<32>(u);                                                                    // [phase: fft_stage2]
     // ---- split the two real spectra (Z[k], conj Z[512-k]) and take |.|^2            // [phase: split_power]
-    const int src = ((16 - k1l) & 15) | (lane & 16);
-    float2* P2 = reinterpret_cast<float2*>(Ebuf) + (lane >> 4) + 2 * k1l;   // P4[k].{xy | zw}, k = k1 + 16 k2
+    const int src = (((16 - k1l) & 15) << 1) | trl;
+    float2* P2 = reinterpret_cast<float2*>(Ebuf) + lane;   // P4[k].{xy | zw}, k = k1 + 16 k2: float2 index 2 k + transform
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
       const float2 zk = u[bitrev_n(k2, 5)];
@@ -312,12 +334,12 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
     }
     __syncwarp();
   }
-  // ---- mel (lanes = bins), log, normalise, mask, store                              // [phase: mel]
+  // ---- mel (lane slots = bins), log, normalise, mask, store                         // [phase: mel]
   const float4* P4 = reinterpret_cast<const float4*>(Ebuf);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= fp.mel_groups) continue;
-    const int m = lane + 32 * i;
+    const int m = L.bin(i);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (f0 < nf) {
       const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
@@ -331,20 +353,25 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       }
     }
     if (m < p.n_mel) {                                                                 // [phase: epilogue_store]
-      float x[4];
+      // v = lg2(max(mel, FLT_EPSILON)) (log output) or mel.  Floored cells take the constant -23 = lg2(FLT_EPSILON):
+      // -23 * float(ln 2) is exactly the float32 log(FLT_EPSILON) of the reference (MUFU.LG2 itself is not exact there)
+      float v[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        x[h] = acc[h];
-        if (AST || p.use_log) {                    // lg2.approx * ln 2; the floor value is the exact float32 log(FLT_EPSILON)
+        v[h] = acc[h];
+        if (AST || p.use_log) {
           float l2;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(acc[h], B200_FLT_EPSILON)));
-          x[h] = acc[h] > B200_FLT_EPSILON ? l2 * 0.69314718055994531f : B200_LOG_FLT_EPSILON;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(acc[h]));
+          v[h] = acc[h] > B200_FLT_EPSILON ? l2 : -23.0f;
         }
       }
       if (STATS) {
 #pragma unroll
         for (int h = 0; h < 4; ++h)
-          if ((f0 + h) < nf) { st_s[i] += (double)x[h]; st_ss[i] += (double)x[h] * (double)x[h]; }
+          if ((f0 + h) < nf) {
+            const float x = v[h] * L.scale(i);                    // STATS: scale = ln 2 (or 1), shift = 0
+            st_s[i] += (double)x; st_ss[i] += (double)x * (double)x;
+          }
       } else {
         float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + t0) * p.n_cols + m
                                  : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + t0;
@@ -353,14 +380,14 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
         if (plain) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(x[h] - L.mean(i), L.scale(i), L.shift(i));
+          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(v[h], L.scale(i), L.shift(i));
         } else {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const int t = t0 + h;
             if (t < row_end) {
-              float y = (f0 + h) < nf ? x[h] : 0.f;                 // H9: pad rows are 0.0 before normalisation
-              y = fmaf(y - L.mean(i), L.scale(i), L.shift(i));
+              // H9: pad rows are 0.0 before normalisation = the folded shift
+              float y = (f0 + h) < nf ? fmaf(v[h], L.scale(i), L.shift(i)) : L.shift(i);
               if (t >= mk0 && t < mk0 + mk1) y = 0.f;
               o[h * ostep] = y;
             }
@@ -410,16 +437,11 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
   for (int j = 0; j < 13; ++j) L.win[j] = (lane + 32 * j < FK_SIZE) ? __ldg(p.window + lane + 32 * j) : 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = lane + 32 * i;
-    L.mstart[i] = (m < p.n_mel) ? __ldg(p.mel_start + m) : 0;
-    L.nmean[i] = 0.f; L.nscale[i] = 1.f; L.nshift[i] = 0.f;
-    if (!STATS && p.n_stats > 0 && m < p.n_mel) {
-      const int si = p.n_stats == 1 ? 0 : m;
-      L.nmean[i] = __ldg(p.mean + si);
-      L.nscale[i] = p.target_std / __ldg(p.std + si);
-      L.nshift[i] = p.target_mean;
-    }
-    if (m >= mk2 && m < mk2 + mk3) { L.nscale[i] = 0.f; L.nshift[i] = 0.f; }   // frequency mask: the whole column is 0.0
+    const bool have = i < fp.mel_groups;
+    const int m = have ? __ldg(fp.mel_slot_bin + lane + 32 * i) : p.n_mel;
+    L.mbin[i] = m;
+    L.mstart[i] = have ? __ldg(fp.mel_slot_start + lane + 32 * i) : 0;
+    fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, L.nscale[i], L.nshift[i]);
   }
   double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
   __syncthreads();
@@ -513,7 +535,7 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
   if (STATS) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int m = lane + 32 * i;
+      const int m = L.mbin[i];
       if (i < fp.mel_groups && m < p.n_mel) {
         atomicAdd(p.sums + m, st_s[i]);
         atomicAdd(p.sums + p.n_cols + m, st_ss[i]);

@@ -190,15 +190,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     if (row < 13) {
       v = (ln + 32 * row < FK_SIZE) ? __ldg(p.window + ln + 32 * row) : 0.f;
     } else {
-      const int i = (row - 13) & 3, kind = (row - 13) >> 2;      // kind 0 mstart, 1 mean, 2 scale, 3 shift
-      const int m = ln + 32 * i;
-      const bool fmask = (m >= mk2 && m < mk2 + mk3);            // frequency mask: the whole column is 0.0
-      const bool norm = !STATS && p.n_stats > 0 && m < p.n_mel;
-      const int si = p.n_stats == 1 ? 0 : m;
-      if (kind == 0) v = __int_as_float((m < p.n_mel) ? __ldg(p.mel_start + m) : 0);
-      else if (kind == 1) v = norm ? __ldg(p.mean + si) : 0.f;
-      else if (kind == 2) v = fmask ? 0.f : (norm ? p.target_std / __ldg(p.std + si) : 1.f);
-      else v = (fmask || !norm) ? 0.f : p.target_mean;
+      const int i = (row - 13) & 3, kind = (row - 13) >> 2;      // kind 0 mstart, 1 mbin, 2 scale, 3 shift
+      const bool have = i < fp.mel_groups;
+      const int m = have ? __ldg(fp.mel_slot_bin + ln + 32 * i) : p.n_mel;
+      float sc, shf;
+      fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, sc, shf);   // frequency mask: the whole column is 0.0
+      if (kind == 0) v = __int_as_float(have ? __ldg(fp.mel_slot_start + ln + 32 * i) : 0);
+      else if (kind == 1) v = __int_as_float(m);
+      else if (kind == 2) v = sc;
+      else v = shf;
     }
     slane[e] = v;
   }
@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     for (int j = 0; j < 13; ++j) L.win[j] = slane[j * 32 + lane];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      L.mstart[i] = __float_as_int(slane[(13 + i) * 32 + lane]);
-      L.nmean[i] = slane[(17 + i) * 32 + lane]; L.nscale[i] = slane[(21 + i) * 32 + lane]; L.nshift[i] = slane[(25 + i) * 32 + lane];
+      L.mstart[i] = __float_as_int(slane[(13 + i) * 32 + lane]); L.mbin[i] = __float_as_int(slane[(17 + i) * 32 + lane]);
+      L.nscale[i] = slane[(21 + i) * 32 + lane]; L.nshift[i] = slane[(25 + i) * 32 + lane];
     }
     double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
     float* Ebuf = ebuf + wf * FK_EBUF;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     if (STATS) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i;
+        const int m = L.mbin[i];
         if (i < fp.mel_groups && m < p.n_mel) {
           atomicAdd(p.sums + m, st_s[i]);
           atomicAdd(p.sums + p.n_cols + m, st_ss[i]);
