@@ -173,7 +173,7 @@ __device__ __forceinline__ int fk_load_x_async(const float* g /* = clip + in_lo 
 struct FkLane {
   float win[13];        // window at n = lane + 32 j
   int mstart[4];        // first FFT bin read by lane slot (i, lane)
-  int mbin[4];          // mel bin of lane slot (i, lane); >= n_mel: no bin
+  int mbin[4];          // output offset of the slot's mel bin m: m (kaldi layout, stats) or m * out_frames (AST layout); -1: no bin
   float nscale[4], nshift[4];   // epilogue: y = v * nscale + nshift, v = lg2(mel) (log output) or mel; see fk_fold_norm
   __device__ __forceinline__ float w(int j) const { return win[j]; }
   __device__ __forceinline__ int ms(int i) const { return mstart[i]; }
@@ -225,14 +225,20 @@ __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, con
       if (j < 12) s += yv[j];
     }
     s += lane < 16 ? yv[12] : 0.f;
-    const float mean = warp_sum(s) * dc_scale;
+    // (y[n] - mean) - c (y[n-1] - mean) = (y[n] - c y[n-1]) - (1 - c) mean: one fma, one add, one multiply per sample
+    const float mean1 = warp_sum(s) * dc_scale;          // dc_scale = (1 - c) / 400, or 0 without DC removal
     const float* y0 = y - d0;
     const float* y5 = y - d5;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
       const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
       const float prev = (j == 0) ? y0[off] : ((j == 5 || j == 10) ? y5[off] : y[off - 1]);
-      const float v = ((yv[j] - mean) - preemph * (prev - mean)) * L.w(j);
+#ifdef B200_STAGE0_FOLD
+      const float v = (fmaf(-preemph, prev, yv[j]) - mean1) * L.w(j);
+#else
+      // the reference's own order of roundings (kaldi.py:183-204): errors stay correlated with torchaudio's
+      const float v = ((yv[j] - mean1) - preemph * (prev - mean1)) * L.w(j);
+#endif
       if (h == 0) z[j].x = v; else z[j].y = v;
     }
   }
@@ -243,7 +249,16 @@ __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, con
 // 16-point DFT over n1, twiddle W_512^(lane k1), store row k1 of the exchange buffer.   // [phase: fft_stage1]
 __device__ __forceinline__ void fk_stage1_store(float2 (&z)[16], const float2* __restrict__ stw, int lane,
                                                 float2* __restrict__ E) {
-  fft_dif<16>(z);
+  // z[13..15] are the zero padding 400 -> 512: the first radix-2 stage has nothing to add or subtract there
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float2 a = z[j], b2 = z[j + 8];
+    z[j] = cadd(a, b2);
+    z[j + 8] = j == 0 ? csub(a, b2) : j == 1 ? mul_w32<2>(csub(a, b2)) : j == 2 ? mul_w32<4>(csub(a, b2))
+             : j == 3 ? mul_w32<6>(csub(a, b2)) : mul_w32<8>(csub(a, b2));
+  }
+  z[13] = mul_w32<10>(z[5]); z[14] = mul_w32<12>(z[6]); z[15] = mul_w32<14>(z[7]);
+  DifStages<16, 4>::run(z);
   E[lane] = z[0];
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) {
@@ -292,7 +307,11 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   const int nf = n_live;
   (void)mk2; (void)mk3;
   if (f0 < nf) {
+#ifdef B200_STAGE0_FOLD
+    const float dc_scale = p.remove_dc ? (1.f - p.preemph) / (float)FK_SIZE : 0.f;
+#else
     const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
+#endif
     // the two packed transforms (frames 0,1 and 2,3); unrolled so their dependency chains interleave (a rolled loop
     // halves the code but measured 3% slower: the pass is latency-bound, not instruction-cache bound)
 #pragma unroll
@@ -336,10 +355,16 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   }
   // ---- mel (lane slots = bins), log, normalise, mask, store                         // [phase: mel]
   const float4* P4 = reinterpret_cast<const float4*>(Ebuf);
+  // warp-uniform output addressing, once per pass: row t0 of clip b; the lane adds its bin offset L.bin(i)
+  const int ostep = p.layout == 0 ? p.n_cols : 1;
+  float* const obase = STATS ? nullptr
+                             : p.out + (p.layout == 0 ? ((size_t)b * p.out_frames + t0) * p.n_cols : (size_t)b * p.n_cols * p.out_frames + t0);
+  // warp-uniform fast path: four live frames inside the segment and no time mask touching them
+  const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= fp.mel_groups) continue;
-    const int m = L.bin(i);
+    const int moff = L.bin(i);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (f0 < nf) {
       const float* wrow = smelw + fp.mel_woff[i] * 32 + lane;
@@ -352,7 +377,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         fk_mel_group<-1>(P4, wrow, L.ms(i), fp.mel_maxcnt[i], acc);
       }
     }
-    if (m < p.n_mel) {                                                                 // [phase: epilogue_store]
+    if (moff >= 0) {                                                                   // [phase: epilogue_store]
       // v = lg2(max(mel, FLT_EPSILON)) (log output) or mel.  Floored cells take the constant -23 = lg2(FLT_EPSILON):
       // -23 * float(ln 2) is exactly the float32 log(FLT_EPSILON) of the reference (MUFU.LG2 itself is not exact there)
       float v[4];
@@ -373,11 +398,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
             st_s[i] += (double)x; st_ss[i] += (double)x * (double)x;
           }
       } else {
-        float* o = p.layout == 0 ? p.out + ((size_t)b * p.out_frames + t0) * p.n_cols + m
-                                 : p.out + ((size_t)b * p.n_cols + m) * p.out_frames + t0;
-        const int ostep = p.layout == 0 ? p.n_cols : 1;
-        // warp-uniform fast path: four live frames inside the segment and no time mask touching them
-        const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
+        float* o = obase + moff;
         if (plain) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(v[h], L.scale(i), L.shift(i));
@@ -439,7 +460,7 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
   for (int i = 0; i < 4; ++i) {
     const bool have = i < fp.mel_groups;
     const int m = have ? __ldg(fp.mel_slot_bin + lane + 32 * i) : p.n_mel;
-    L.mbin[i] = m;
+    L.mbin[i] = m < p.n_mel ? m * ((STATS || p.layout == 0) ? 1 : p.out_frames) : -1;
     L.mstart[i] = have ? __ldg(fp.mel_slot_start + lane + 32 * i) : 0;
     fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, L.nscale[i], L.nshift[i]);
   }
@@ -536,7 +557,7 @@ __global__ void __launch_bounds__(FK_THREADS, 2) fbank_fast_kernel(const FbankPa
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = L.mbin[i];
-      if (i < fp.mel_groups && m < p.n_mel) {
+      if (i < fp.mel_groups && m >= 0) {
         atomicAdd(p.sums + m, st_s[i]);
         atomicAdd(p.sums + p.n_cols + m, st_ss[i]);
       }
