@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -535,14 +536,86 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     if (kenv && strcmp(kenv, "fast") == 0) ok = false;
     if (int rc = dev_copy(wt.data(), wt.size() * 4, (const void**)&f.ws_taps)) return rc;
     if (int rc = dev_copy(wk.data(), wk.size() * 4, (const void**)&f.ws_k0g)) return rc;
+    // ---- resampler mode per rate: 1 = 441 -> 160 (above), 2 = 3 -> 1, 3 = 441 -> 320, 0 = per-sample loop / identity
+    for (int i = 0; i < B200_MAX_RATES; ++i) f.ws_mode[i] = 0;
+    if (ok) f.ws_mode[f.fast_rate_id] = 1;
+    std::vector<float> t48(4 * WS_P48, 0.f), t22((size_t)2 * 32 * FK_RP * WS_LT22, 0.f);
+    std::vector<int> k22(64, 0);
+    const bool tuned_other = !(getenv("B200FBANK_WS_GENERIC_RATES") && atoi(getenv("B200FBANK_WS_GENERIC_RATES")));
+    for (size_t ri = 0; ri < p->rates.size() && tuned_other; ++ri) {
+      const RateHost& r = p->rates[ri];
+      if (r.identity) continue;
+      if (r.orig == 3 && r.nw == 1 && r.width == WS_W48 && r.klen == 2 * WS_W48 + 3) {
+        // 3 -> 1: tap pairs for even window starts (h[2i], h[2i+1]) and odd ones (h[2i-1], h[2i])
+        auto h = [&](int k) { return (k >= 0 && k < r.klen) ? r.dense[k] : 0.f; };
+        for (int i = 0; i < WS_P48; ++i) {
+          t48[2 * i] = h(2 * i); t48[2 * i + 1] = h(2 * i + 1);
+          t48[2 * (WS_P48 + i)] = h(2 * i - 1); t48[2 * (WS_P48 + i) + 1] = h(2 * i);
+        }
+        f.ws_mode[ri] = 2;
+      } else if (r.orig == FK_ORIG && r.nw == 2 * FK_NEW && r.width == WS_W22) {
+        // 441 -> 320: per hop parity and lane, 5 phases x WS_LT22 taps from a window start chosen inside the lane's slack
+        // so that the 32 starts of a warp are distinct mod 32 (bipartite matching lanes -> banks)
+        bool fit = true;
+        for (int par = 0; par < 2 && fit; ++par) {
+          int lo[32], hi[32], owner[32], pick[32];
+          for (int g = 0; g < 32 && fit; ++g) {
+            lo[g] = 0; hi[g] = r.klen;
+            for (int q = 0; q < FK_RP; ++q) {
+              const float* d = &r.dense[(size_t)(160 * par + FK_RP * g + q) * r.klen];
+              int a = r.klen, bb = -1;
+              for (int k = 0; k < r.klen; ++k)
+                if (std::fabs(d[k]) > 1e-25f) { a = std::min(a, k); bb = std::max(bb, k); }
+              hi[g] = std::min(hi[g], a - ws_off22(q));
+              lo[g] = std::max(lo[g], bb - ws_off22(q) - WS_LT22 + 1);
+            }
+            hi[g] = std::min(hi[g], r.klen + 8 - (ws_off22(FK_RP - 1) + WS_LT22));   // stays inside the staged input tile
+            if (lo[g] > hi[g]) fit = false;
+          }
+          if (!fit) break;
+          for (int b = 0; b < 32; ++b) owner[b] = -1;
+          // Kuhn's augmenting paths; visited[] per search
+          std::vector<char> visited(32);
+          std::function<bool(int)> place = [&](int g) -> bool {
+            for (int k = hi[g]; k >= lo[g]; --k) {
+              const int b = k & 31;
+              if (visited[b]) continue;
+              visited[b] = 1;
+              if (owner[b] < 0 || place(owner[b])) { owner[b] = g; pick[g] = k; return true; }
+            }
+            return false;
+          };
+          for (int g = 0; g < 32; ++g) {
+            std::fill(visited.begin(), visited.end(), 0);
+            if (!place(g)) pick[g] = hi[g];          // no perfect matching: keep a legal start, accept the conflict
+          }
+          for (int g = 0; g < 32; ++g) {
+            k22[par * 32 + g] = pick[g];
+            for (int q = 0; q < FK_RP; ++q) {
+              const float* d = &r.dense[(size_t)(160 * par + FK_RP * g + q) * r.klen];
+              for (int j = 0; j < WS_LT22; ++j) {
+                const int k = pick[g] + ws_off22(q) + j;
+                t22[((size_t)(par * 32 + g) * FK_RP + q) * WS_LT22 + j] = (k >= 0 && k < r.klen) ? d[k] : 0.f;
+              }
+            }
+          }
+        }
+        if (fit) f.ws_mode[ri] = 3;
+      }
+    }
+    if (int rc = dev_copy(t48.data(), t48.size() * 4, (const void**)&f.ws_t48)) return rc;
+    if (int rc = dev_copy(t22.data(), t22.size() * 4, (const void**)&f.ws_t22)) return rc;
+    if (int rc = dev_copy(k22.data(), k22.size() * 4, (const void**)&f.ws_k22)) return rc;
     p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32) * 4 + 128;
     // rates without the 44.1 kHz structure still run through this kernel's per-sample path
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;
-    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-    CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    f.ws_multi = 0;
+    for (int i = 0; i < B200_MAX_RATES; ++i) f.ws_multi |= (f.ws_mode[i] >= 2);
+#define B200_WS_ATTR(S, A, M) CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<S, A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin))
+    B200_WS_ATTR(false, false, false); B200_WS_ATTR(false, true, false); B200_WS_ATTR(true, false, false); B200_WS_ATTR(true, true, false);
+    B200_WS_ATTR(false, false, true); B200_WS_ATTR(false, true, true); B200_WS_ATTR(true, false, true); B200_WS_ATTR(true, true, true);
+#undef B200_WS_ATTR
   }
   const char* seg = getenv("B200FBANK_SEG");
   f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 0;      // 0 = pick per launch (pick_seg_frames)
@@ -750,8 +823,13 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
-    if (f.ast_bank) b200::fbank_ws_kernel<false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
-    else b200::fbank_ws_kernel<false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+    if (f.ws_multi) {
+      if (f.ast_bank) b200::fbank_ws_kernel<false, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+      else b200::fbank_ws_kernel<false, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+    } else {
+      if (f.ast_bank) b200::fbank_ws_kernel<false, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+      else b200::fbank_ws_kernel<false, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+    }
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames);
@@ -838,8 +916,13 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
     const int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
-    if (f.ast_bank) b200::fbank_ws_kernel<true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
-    else b200::fbank_ws_kernel<true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+    if (f.ws_multi) {
+      if (f.ast_bank) b200::fbank_ws_kernel<true, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+      else b200::fbank_ws_kernel<true, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+    } else {
+      if (f.ast_bank) b200::fbank_ws_kernel<true, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+      else b200::fbank_ws_kernel<true, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
+    }
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, max_frames);

@@ -68,6 +68,14 @@ struct FastParams {
   const float* ws_taps;   // [32][5][36]
   const int* ws_k0g;      // [32]
   int ws_ok;
+  // resampler mode of each entry of the rate table (fbank_ws.cuh): 0 per-sample loop / identity, 1 = 441 -> 160,
+  // 2 = 3 -> 1 (ws_t48: [2][21] tap pairs, even / odd window starts), 3 = 441 -> 320 (ws_t22: [2 parities][32][5][20],
+  // ws_k22: [2][32] window starts)
+  int ws_mode[B200_MAX_RATES];
+  int ws_multi;           // some entry has mode >= 2: launch the MULTI instantiation
+  const float* ws_t48;
+  const float* ws_t22;
+  const int* ws_k22;
 };
 
 // Copy x[in_lo, in_lo + nx) of the clip into A[sh + i]; returns sh (0..3), chosen so that

@@ -41,7 +41,13 @@ constexpr int WS_SLOTS = 3;
 constexpr int WS_RING_ROWS = 32 * WS_SLOTS;                   // 96 hops
 constexpr int WS_MIRROR = 6;                                  // rows 96..101 repeat rows 0..5
 constexpr int WS_RING_FLOATS = (WS_RING_ROWS + WS_MIRROR) * FK_SHIFT;   // 16320
-constexpr int WS_XFLOATS = 14160;                             // 31*441 + 475 + 8 slack + 3 shift, multiple of 4
+#ifndef B200_WS_XFLOATS
+#define B200_WS_XFLOATS 15424
+#endif
+constexpr int WS_XFLOATS = B200_WS_XFLOATS;                             // 48 kHz chunk: 3*(32*160 - 1) + 41 + 8 slack + 3 shift (44.1 kHz: 31*441 + 475 + 11), multiple of 32
+constexpr int WS_W48 = 19, WS_P48 = 21;                       // 3 -> 1: width 19, 41 taps = 21 pairs (one zero)
+constexpr int WS_W22 = 9, WS_LT22 = 20;                       // 441 -> 320: width 9, 16-17 taps per phase kept as 20
+__host__ __device__ constexpr int ws_off22(int r) { return r < 2 ? 0 : r == 2 ? 2 : 4; }
 constexpr int WS_LT = 36;                                     // taps per phase (34 non-zero + even alignment)
 constexpr int WS_GROUP_FLOATS = FK_RP * WS_LT;                // 180
 
@@ -134,7 +140,9 @@ __device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, i
   fk_cp_async_wait_all();
 }
 
-template <bool STATS, bool AST>
+// MULTI: the 48 kHz / 22.05 kHz resampler modes are compiled in (plans whose rate table needs them); single-rate
+// 44.1 kHz plans run the lean instantiation
+template <bool STATS, bool AST, bool MULTI>
 __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankParams p, const FastParams fp) {   // [phase: ws_setup]
   extern __shared__ __align__(16) float smem[];
   float* xbuf = smem;                                            // [WS_XFLOATS] input chunk (R warps only)
@@ -214,14 +222,46 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 
   if (is_r) {
     // =============================== R warps: resampler ==========================================
+    // mode 1: 441 -> 160 (44.1 kHz), 2: 3 -> 1 (48 kHz), 3: 441 -> 320 (22.05 kHz): register-resident taps, one TMA
+    // bulk copy per chunk; mode 0: any other ratio (per-sample loop) or no resampling at all
     const int rid = p.rate_id ? p.rate_id[b] : 0;
-    const bool fast = (rid == fp.fast_rate_id);
+    const int mode = fp.ws_mode[rid];
     const int rt = tid;                                          // 0..127
     const int rw = warp;                                         // R warp index
     const int g = lane;
+    unsigned x_parity = 0;
+    // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy
+    auto stage_x = [&](int64_t in_lo, int nx) -> int {
+      const float* gsrc = c.wav + in_lo;
+      const int sh = ws_shift(gsrc);
+      if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
+        if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
+        ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
+        x_parity ^= 1u;
+      } else {
+        ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+        ws_bar_r();
+      }
+      return sh;
+    };
+    auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {
+      float* o = rb + q * FK_SHIFT + FK_RP * g;
+#pragma unroll
+      for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
+      if (slot == 0 && q < WS_MIRROR) {
+        float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
+#pragma unroll
+        for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
+      }
+    };
+#ifdef B200_WS_TIMING
+    long long tc_ = 0;
+#endif
+    // ---------------- 441 -> 160: lane = 5 phases, 180 taps in registers, hop rotation (see the header) ----------
+    // (T, k0, skew live at branch scope: ptxas schedules the hop loop 1-2 % better than with block-local ones)
     unsigned long long T[FK_RP][WS_LT / 2];
     int k0 = 0, skew = 0;
-    if (fast) {
+    if (mode == 1) {
       const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
 #pragma unroll
       for (int r = 0; r < FK_RP; ++r)
@@ -238,32 +278,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #pragma unroll
         for (int jj = 0; jj < WS_LT / 2; ++jj) T[r][jj] = 0ull;
     }
-    unsigned x_parity = 0;
-#ifdef B200_WS_TIMING
-    long long tc_ = 0;
-#endif
-    for (int ch = 0; ch < n_chunks; ++ch) {                      // [phase: ws_resample_loop]
-      const int slot = ch % WS_SLOTS;
-      float* rb = ring + slot * 32 * FK_SHIFT;
-      int nh = last_hop - 32 * ch + 1;                           // hops of this chunk anyone reads
-      nh = nh > 32 ? 32 : nh;
-      const int64_t hop0 = (int64_t)row_begin + 32 * ch;         // absolute hop (= 16 kHz sample / 160) of ring row 0 of the slot
-      if (fast) {
-        const int64_t in_lo = hop0 * FK_ORIG - FK_WIDTH;
-        const int nx = (nh - 1) * FK_ORIG + FK_KLEN + 8;
-        const float* gsrc = c.wav + in_lo;
-        const int sh = ws_shift(gsrc);
+    if (mode == 1) {
+      for (int ch = 0; ch < n_chunks; ++ch) {                    // [phase: ws_resample_loop]
+        const int slot = ch % WS_SLOTS;
+        float* rb = ring + slot * 32 * FK_SHIFT;
+        int nh = last_hop - 32 * ch + 1;                         // hops of this chunk anyone reads
+        nh = nh > 32 ? 32 : nh;
+        const int64_t hop0 = (int64_t)row_begin + 32 * ch;       // absolute hop (= 16 kHz sample / 160) of ring row 0 of the slot
 #ifdef B200_WS_TIMING
         const long long ta_ = clock64();
 #endif
-        if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {           // interior chunk: one TMA bulk copy
-          if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
-          ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
-          x_parity ^= 1u;
-        } else {
-          ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
-          ws_bar_r();
-        }
+        const int sh = stage_x(hop0 * FK_ORIG - FK_WIDTH, (nh - 1) * FK_ORIG + FK_KLEN + 8);
 #ifdef B200_WS_TIMING
         const long long tb_ = clock64();
         WS_TACC(0, ta_);
@@ -280,32 +305,121 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
             const int q = (WS_R_ITERS * rw + i + skew) & 31;
             float y[FK_RP];
             ws_resample_hop(xs + q * FK_ORIG, T, y);
-            float* o = rb + q * FK_SHIFT + FK_RP * g;
-#pragma unroll
-            for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
-            if (slot == 0 && q < WS_MIRROR) {
-              float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
-#pragma unroll
-              for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
-            }
+            put_hop(rb, slot, q, y);
           }
         } else {                                                 // short tail chunk: hop = warp, warp + 4
 #pragma unroll 1
           for (int q = rw; q < nh; q += WS_R_WARPS) {
             float y[FK_RP];
             ws_resample_hop(xs + q * FK_ORIG, T, y);
-            float* o = rb + q * FK_SHIFT + FK_RP * g;
-#pragma unroll
-            for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
-            if (slot == 0 && q < WS_MIRROR) {
-              float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
-#pragma unroll
-              for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
-            }
+            put_hop(rb, slot, q, y);
           }
         }
-      } else {
-        // other rates: per-sample polyphase loop (or plain copy) into the same ring slot
+#ifdef B200_WS_TIMING
+        WS_TACC(2, tc_); if (lane == 0) atomicAdd(&g_ws_timing[3], 1ull);
+#endif
+        ws_mbar_arrive(bars + slot);                             // full[slot]: release the 32 hops to the F warps
+        ws_bar_r();                                              // everyone is done with xbuf before the next load
+      }
+    } else if (MULTI && mode == 2) {
+      // ---------------- 3 -> 1 (48 kHz): ONE phase of 41 taps shared by every lane; lane = outputs 5g..5g+4 of a hop,
+      // whose windows start 3 samples apart: even starts pair the taps as (h[2i], h[2i+1]), odd starts as (h[2i-1], h[2i]).
+      // Lanes read x at stride 15 (odd): conflict free without any rotation.                 // [phase: ws_resample_48k]
+      unsigned long long He[WS_P48], Ho[WS_P48];
+      {
+        const float2* tp = reinterpret_cast<const float2*>(fp.ws_t48);
+#pragma unroll
+        for (int i = 0; i < WS_P48; ++i) {
+          const float2 e = __ldg(tp + i), o = __ldg(tp + WS_P48 + i);
+          He[i] = ws_pack(e.x, e.y); Ho[i] = ws_pack(o.x, o.y);
+        }
+      }
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int slot = ch % WS_SLOTS;
+        float* rb = ring + slot * 32 * FK_SHIFT;
+        int nh = last_hop - 32 * ch + 1;
+        nh = nh > 32 ? 32 : nh;
+        const int64_t hop0 = (int64_t)row_begin + 32 * ch;
+        const int sh = stage_x(hop0 * (3 * FK_SHIFT) - WS_W48, (nh * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
+        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+        const float* xs = xbuf + sh + 3 * FK_RP * g;
+#pragma unroll 1
+        for (int q = rw; q < nh; q += WS_R_WARPS) {
+          const float* xq = xs + q * (3 * FK_SHIFT);
+          unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+          for (int j = 0; j < WS_P48 + 6; ++j) {                 // x pairs (2j, 2j+1); phase r starts at pair {0,1,3,4,6}[r]
+            const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
+            if (j < WS_P48) acc[0] = ws_fma2(xp, He[j], acc[0]);
+            if (j >= 1 && j < WS_P48 + 1) acc[1] = ws_fma2(xp, Ho[j - 1], acc[1]);
+            if (j >= 3 && j < WS_P48 + 3) acc[2] = ws_fma2(xp, He[j - 3], acc[2]);
+            if (j >= 4 && j < WS_P48 + 4) acc[3] = ws_fma2(xp, Ho[j - 4], acc[3]);
+            if (j >= 6) acc[4] = ws_fma2(xp, He[j - 6], acc[4]);
+          }
+          float y[FK_RP];
+#pragma unroll
+          for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
+          put_hop(rb, slot, q, y);
+        }
+        ws_mbar_arrive(bars + slot);
+        ws_bar_r();
+      }
+    } else if (MULTI && mode == 3) {
+      // ---------------- 441 -> 320 (22.05 kHz): 320 phases = two hops; even R warps hold the taps of phases 0..159 (even
+      // hops), odd R warps those of 160..319; lane = 5 phases x 20 taps.  The host picks each lane's window start inside
+      // its slack so that the 32 starts are distinct mod 32: conflict free without rotation.   // [phase: ws_resample_22k]
+      const int par = rw & 1;
+      unsigned long long T[FK_RP][WS_LT22 / 2];
+      {
+        const float2* tp = reinterpret_cast<const float2*>(fp.ws_t22 + (size_t)(par * 32 + g) * (FK_RP * WS_LT22));
+#pragma unroll
+        for (int r = 0; r < FK_RP; ++r)
+#pragma unroll
+          for (int jj = 0; jj < WS_LT22 / 2; ++jj) {
+            const float2 t2 = __ldg(tp + r * (WS_LT22 / 2) + jj);
+            T[r][jj] = ws_pack(t2.x, t2.y);
+          }
+      }
+      const int k0 = __ldg(fp.ws_k22 + par * 32 + g);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int slot = ch % WS_SLOTS;
+        float* rb = ring + slot * 32 * FK_SHIFT;
+        int nh = last_hop - 32 * ch + 1;
+        nh = nh > 32 ? 32 : nh;
+        const int64_t hop0 = (int64_t)row_begin + 32 * ch;       // even: segments start on multiples of 32 frames
+        const int np = (nh + 1) >> 1;                            // periods (pairs of hops) of this chunk
+        const int sh = stage_x((hop0 >> 1) * FK_ORIG - WS_W22, (np - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
+        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+        const float* xs = xbuf + sh + k0;
+#pragma unroll 1
+        for (int Q = rw >> 1; 2 * Q + par < nh; Q += WS_R_WARPS / 2) {
+          const float* xq = xs + Q * FK_ORIG;
+          unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+          for (int j = 0; j < WS_LT22 / 2 + 2; ++j) {            // phase r starts at pair ws_off22(r) / 2
+            const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
+#pragma unroll
+            for (int r = 0; r < FK_RP; ++r) {
+              const int i = j - ws_off22(r) / 2;
+              if (i >= 0 && i < WS_LT22 / 2) acc[r] = ws_fma2(xp, T[r][i], acc[r]);
+            }
+          }
+          float y[FK_RP];
+#pragma unroll
+          for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
+          put_hop(rb, slot, 2 * Q + par, y);
+        }
+        ws_mbar_arrive(bars + slot);
+        ws_bar_r();
+      }
+    } else {
+      // ---------------- other rates: per-sample polyphase loop (or plain copy) into the same ring slot ----------------
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int slot = ch % WS_SLOTS;
+        float* rb = ring + slot * 32 * FK_SHIFT;
+        int nh = last_hop - 32 * ch + 1;
+        nh = nh > 32 ? 32 : nh;
+        const int64_t hop0 = (int64_t)row_begin + 32 * ch;
         if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
         const int total = nh * FK_SHIFT;
         const int64_t s_base = hop0 * FK_SHIFT;                  // absolute resampled index of slot row 0
@@ -343,12 +457,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
             }
           }
         }
+        ws_mbar_arrive(bars + slot);                             // full[slot]: release the 32 hops to the F warps
+        ws_bar_r();                                              // everyone is done with xbuf before the next load
       }
-#ifdef B200_WS_TIMING
-      if (fast) { WS_TACC(2, tc_); if (lane == 0) atomicAdd(&g_ws_timing[3], 1ull); }
-#endif
-      ws_mbar_arrive(bars + slot);                               // full[slot]: release the 32 hops to the F warps
-      ws_bar_r();                                                // everyone is done with xbuf before the next load
     }
   } else {
     // =============================== F warps: frames =============================================
