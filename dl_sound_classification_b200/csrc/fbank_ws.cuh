@@ -244,6 +244,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       }
       return sh;
     };
+    // warm the L2 with the NEXT chunk's input while this one is being resampled: the xbuf itself cannot be loaded ahead
+    // (every lane visits every hop of the chunk), but a bulk L2 prefetch takes the DRAM latency out of the next TMA copy
+    auto prefetch_x = [&](int64_t in_lo, int nx) {
+      if (rt == 32 && in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
+        const float* gsrc = c.wav + in_lo;
+        const int sh = ws_shift(gsrc);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc - sh), "r"((unsigned)(((nx + sh + 3) >> 2) << 4)) : "memory");
+      }
+    };
     auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {
       float* o = rb + q * FK_SHIFT + FK_RP * g;
 #pragma unroll
@@ -288,6 +297,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #ifdef B200_WS_TIMING
         const long long ta_ = clock64();
 #endif
+        if (ch + 1 < n_chunks) {
+          int nh2 = last_hop - 32 * (ch + 1) + 1;
+          nh2 = nh2 > 32 ? 32 : nh2;
+          prefetch_x((hop0 + 32) * FK_ORIG - FK_WIDTH, (nh2 - 1) * FK_ORIG + FK_KLEN + 8);
+        }
         const int sh = stage_x(hop0 * FK_ORIG - FK_WIDTH, (nh - 1) * FK_ORIG + FK_KLEN + 8);
 #ifdef B200_WS_TIMING
         const long long tb_ = clock64();
@@ -340,6 +354,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         int nh = last_hop - 32 * ch + 1;
         nh = nh > 32 ? 32 : nh;
         const int64_t hop0 = (int64_t)row_begin + 32 * ch;
+        if (ch + 1 < n_chunks) {
+          int nh2 = last_hop - 32 * (ch + 1) + 1;
+          nh2 = nh2 > 32 ? 32 : nh2;
+          prefetch_x((hop0 + 32) * (3 * FK_SHIFT) - WS_W48, (nh2 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
+        }
         const int sh = stage_x(hop0 * (3 * FK_SHIFT) - WS_W48, (nh * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
         if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
         const float* xs = xbuf + sh + 3 * FK_RP * g;
@@ -388,6 +407,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         nh = nh > 32 ? 32 : nh;
         const int64_t hop0 = (int64_t)row_begin + 32 * ch;       // even: segments start on multiples of 32 frames
         const int np = (nh + 1) >> 1;                            // periods (pairs of hops) of this chunk
+        if (ch + 1 < n_chunks) {
+          int nh2 = last_hop - 32 * (ch + 1) + 1;
+          nh2 = nh2 > 32 ? 32 : nh2;
+          prefetch_x(((hop0 >> 1) + 16) * FK_ORIG - WS_W22, (((nh2 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
+        }
         const int sh = stage_x((hop0 >> 1) * FK_ORIG - WS_W22, (np - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
         if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
         const float* xs = xbuf + sh + k0;
