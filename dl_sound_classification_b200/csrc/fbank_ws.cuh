@@ -116,7 +116,7 @@ __device__ __forceinline__ int ws_shift(const float* g) { return (int)(((uintptr
 // R-side load of an EDGE chunk x[in_lo, in_lo+nx) (128 threads): whole lines inside the clip go through cp.async,
 // lines that straddle a clip edge are assembled by hand, samples outside the clip are zeros (the zero padding
 // of torchaudio's conv, functional.py:1424).  Interior chunks use one TMA bulk copy instead.   // [phase: ws_load]
-__device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, int nx, int sh, float* xbuf, int rt) {
+__device__ __forceinline__ void ws_load_edge_issue(const ClipInfo& c, int64_t in_lo, int nx, int sh, float* xbuf, int rt) {
   const float* g = c.wav + in_lo;
   const float* g0 = g - sh;                                  // 16-B aligned; slot v <-> elements i = 4v - sh + {0..3}
   const int nvec = (nx + sh + 3) >> 2;
@@ -137,6 +137,9 @@ __device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, i
       *reinterpret_cast<float4*>(xbuf + 4 * v) = x;
     }
   }
+}
+__device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, int nx, int sh, float* xbuf, int rt) {
+  ws_load_edge_issue(c, in_lo, nx, sh, xbuf, rt);
   fk_cp_async_wait_all();
 }
 
@@ -181,6 +184,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     }
     ws_mbar_init(bars + 2 * WS_SLOTS, 1);                        // xfull: TMA transaction barrier of the input chunk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the R warps start the input of chunk 0 before anything else: it then arrives while the tables are staged and the
+  // taps are loaded (chunk 0 of a clip starts in the zero padding, so it normally takes the cp.async edge path)
+  int pre_sh = -1;
+  bool pre_tma = false;
+  if (warp < WS_R_WARPS && n_chunks > 0) {
+    const int mode0 = fp.ws_mode[p.rate_id ? p.rate_id[b] : 0];
+    const int nh0 = last_hop + 1 > 32 ? 32 : last_hop + 1;
+    int64_t lo0 = 0;
+    int nx0 = 0;
+    if (mode0 == 1) { lo0 = (int64_t)row_begin * FK_ORIG - FK_WIDTH; nx0 = (nh0 - 1) * FK_ORIG + FK_KLEN + 8; }
+    else if (MULTI && mode0 == 2) { lo0 = (int64_t)row_begin * (3 * FK_SHIFT) - WS_W48; nx0 = (nh0 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8; }
+    else if (MULTI && mode0 == 3) { lo0 = (int64_t)(row_begin >> 1) * FK_ORIG - WS_W22; nx0 = (((nh0 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8; }
+    if (nx0 > 0) {
+      pre_sh = ws_shift(c.wav + lo0);
+      pre_tma = lo0 >= 4 && lo0 + nx0 + 4 <= c.n_in;
+      if (pre_tma) {
+        if (tid == 0) ws_tma_load(xbuf, c.wav + lo0 - pre_sh, (unsigned)(((nx0 + pre_sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
+      } else {
+        ws_load_edge_issue(c, lo0, nx0, pre_sh, xbuf, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
   }
   if (n_real_pass > 0) {
     for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
@@ -232,6 +258,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     unsigned x_parity = 0;
     // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy
     auto stage_x = [&](int64_t in_lo, int nx) -> int {
+      if (pre_sh >= 0) {                                          // chunk 0: issued at the top of the kernel
+        const int sh0 = pre_sh;
+        pre_sh = -1;
+        if (pre_tma) {
+          ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
+          x_parity ^= 1u;
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          ws_bar_r();
+        }
+        return sh0;
+      }
       const float* gsrc = c.wav + in_lo;
       const int sh = ws_shift(gsrc);
       if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
