@@ -703,6 +703,25 @@ int pick_seg_frames(const b200::FastParams& f, int B, int frames, int slots = 29
   return 32;
 }
 
+// Persistent launch of the warp-specialised kernel: dense batches (equal clips) larger than one wave run as one CTA
+// per SM that walks its items with the R/F pipeline carried across clip boundaries; ragged batches keep one CTA per
+// item so the hardware scheduler balances the uneven clips.  B200FBANK_PERSIST=0/1 overrides.
+void ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastParams& f, int64_t& grid) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms = n;
+  }
+  (void)p;
+  const char* env = getenv("B200FBANK_PERSIST");
+  bool persist = d_offsets == nullptr;
+  if (env) persist = atoi(env) != 0;
+  f.ws_persist = (persist && grid > sms) ? 1 : 0;
+  if (f.ws_persist) grid = sms;
+}
+
 int check_device_call(const b200fbank_plan* p, const void* wav, const int64_t* offsets, int64_t clip_samples, int B) {
   if (!p) return fail(B200FBANK_ERR_INVALID, "plan is NULL");
   if (p->device < 0) return fail(B200FBANK_ERR_NO_DEVICE, "host-only plan (device=-1): no CPU compute path exists");
@@ -821,8 +840,9 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames, 148);
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
-    const int64_t grid = (int64_t)B * f.segs;
+    int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
+    ws_pick_grid(p, d_offsets, f, grid);
     if (f.ws_multi) {
       if (f.ast_bank) b200::fbank_ws_kernel<false, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
       else b200::fbank_ws_kernel<false, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
@@ -914,8 +934,9 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, max_frames, 148);
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
-    const int64_t grid = (int64_t)B * f.segs;
+    int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
+    ws_pick_grid(p, d_offsets, f, grid);
     if (f.ws_multi) {
       if (f.ast_bank) b200::fbank_ws_kernel<true, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
       else b200::fbank_ws_kernel<true, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);

@@ -73,6 +73,7 @@ struct FastParams {
   // ws_k22: [2][32] window starts)
   int ws_mode[B200_MAX_RATES];
   int ws_multi;           // some entry has mode >= 2: launch the MULTI instantiation
+  int ws_persist;         // per launch: 1 = grid of #SMs CTAs looping over the items (dense batches), 0 = one item per CTA
   const float* ws_t48;
   const float* ws_t22;
   const int* ws_k22;

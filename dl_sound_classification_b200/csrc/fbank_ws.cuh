@@ -93,7 +93,7 @@ __device__ __forceinline__ unsigned long long ws_fma2(unsigned long long a, unsi
 }
 
 // One hop of one lane: 5 phases from 46 input samples; T[r][jj] = taps (2jj, 2jj+1) of phase r.   // [phase: ws_resample]
-__device__ __forceinline__ void ws_resample_hop(const float* __restrict__ xs, const unsigned long long (&T)[FK_RP][WS_LT / 2],
+__device__ __forceinline__ void ws_resample_hop(const float* __restrict__ xs, const unsigned long long (&T)[FK_RP * WS_LT / 2],
                                                 float (&y)[FK_RP]) {
   unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
 #pragma unroll
@@ -102,7 +102,7 @@ __device__ __forceinline__ void ws_resample_hop(const float* __restrict__ xs, co
 #pragma unroll
     for (int r = 0; r < FK_RP; ++r) {
       const int j = u - ws_off(r);
-      if (j >= 0 && j < WS_LT) acc[r] = ws_fma2(xp, T[r][j >> 1], acc[r]);
+      if (j >= 0 && j < WS_LT) acc[r] = ws_fma2(xp, T[r * (WS_LT / 2) + (j >> 1)], acc[r]);
     }
   }
 #pragma unroll
@@ -143,8 +143,44 @@ __device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, i
   fk_cp_async_wait_all();
 }
 
+// Geometry of one work item = one segment of one clip (recomputed by each role from the item number).
+struct WsItem {
+  int b, seg, row_begin, row_end, m_eff;
+  int n_pass;        // passes that own output rows
+  int n_real;        // real frames of the segment
+  int last_hop;      // last ring row (relative hop) any pass reads
+  int n_chunks;      // 32-hop chunks the R warps produce
+  int pp_total;      // pass slots of the item: max(n_pass, 8 n_chunks); slots >= n_pass only release ring rows
+  bool valid;
+};
+template <bool STATS>
+__device__ __forceinline__ WsItem ws_item(const FbankParams& p, const FastParams& fp, const ClipInfo& c, int item) {
+  WsItem it;
+  it.b = item / fp.segs;
+  it.seg = item - it.b * fp.segs;
+  const int cap = STATS ? p.max_frames : p.out_frames;
+  it.m_eff = (int)(c.m < cap ? c.m : cap);
+  it.row_begin = it.seg * fp.seg_frames;
+  it.row_end = (it.row_begin + fp.seg_frames < cap) ? it.row_begin + fp.seg_frames : cap;
+  it.valid = it.row_begin < cap && !(STATS && it.row_begin >= it.m_eff);
+  const int rows = it.row_end - it.row_begin;
+  it.n_pass = (rows + 3) >> 2;
+  int n_real = it.m_eff - it.row_begin;
+  it.n_real = n_real < 0 ? 0 : (n_real > rows ? rows : n_real);
+  const int n_real_pass = (it.n_real + 3) >> 2;                  // passes with at least one real frame
+  it.last_hop = 4 * (n_real_pass - 1) + 5;
+  it.n_chunks = n_real_pass > 0 ? it.last_hop / 32 + 1 : 0;
+  it.pp_total = it.n_pass > 8 * it.n_chunks ? it.n_pass : 8 * it.n_chunks;
+  return it;
+}
+
 // MULTI: the 48 kHz / 22.05 kHz resampler modes are compiled in (plans whose rate table needs them); single-rate
-// 44.1 kHz plans run the lean instantiation
+// 44.1 kHz plans run the lean instantiation.
+//
+// Persistent form (fp.ws_persist, dense batches): grid = #SMs, CTA x works on items x, x + grid, ...; the R/F pipeline
+// runs straight through the item boundaries (ring slots, barrier phases and the pass -> warp assignment are numbered
+// per CTA, not per clip), so the R warps resample the head of the next clip while the F warps still finish the tail of
+// the current one.  Otherwise grid = #items and every CTA takes exactly one.
 template <bool STATS, bool AST, bool MULTI>
 __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankParams p, const FastParams fp) {   // [phase: ws_setup]
   extern __shared__ __align__(16) float smem[];
@@ -153,95 +189,45 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   float* ebuf = ring + WS_RING_FLOATS;                           // [8][FK_EBUF] exchange / power buffers of the F warps
   float2* stw = reinterpret_cast<float2*>(ebuf + WS_F_WARPS * FK_EBUF);   // [512]
   float* smelw = reinterpret_cast<float*>(stw + 512);            // [mel_rows * 32]
-  float* slane = smelw + ((fp.mel_rows * 32 + 3) & ~3);          // [FK_LANE_ROWS][32] per-lane constants of the F warps
+  float* slane = smelw + ((fp.mel_rows * 32 + 3) & ~3);          // [FK_LANE_ROWS][32] static per-lane constants of the F warps
   uint64_t* bars = reinterpret_cast<uint64_t*>(slane + FK_LANE_ROWS * 32);   // full[3], empty[3], xfull
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / fp.segs;
-  const int seg = blockIdx.x - b * fp.segs;
-  const ClipInfo c = clip_info(p, b);
-  const int cap = STATS ? p.max_frames : p.out_frames;
-  const int m_eff = (int)(c.m < cap ? c.m : cap);
-  const int row_begin = seg * fp.seg_frames;
-  if (row_begin >= cap) return;
-  const int row_end = (row_begin + fp.seg_frames < cap) ? row_begin + fp.seg_frames : cap;
-  if (!STATS && seg == 0 && tid == 0 && p.n_frames_out) p.n_frames_out[b] = m_eff;
-  if (STATS && row_begin >= m_eff) return;
-
-  const int rows = row_end - row_begin;
-  const int n_pass = (rows + 3) >> 2;                            // passes that own output rows
-  int n_real = m_eff - row_begin;
-  n_real = n_real < 0 ? 0 : (n_real > rows ? rows : n_real);
-  const int n_real_pass = (n_real + 3) >> 2;                     // passes with at least one real frame
-  const int last_hop = 4 * (n_real_pass - 1) + 5;                // last ring row (relative hop) any pass reads
-  const int n_chunks = n_real_pass > 0 ? last_hop / 32 + 1 : 0;
+  const int total = p.B * fp.segs;
+  const int stride = fp.ws_persist ? (int)gridDim.x : total;     // items of this CTA: blockIdx.x, + stride, ...
 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < WS_SLOTS; ++s) {
       ws_mbar_init(bars + s, WS_R_THREADS);                      // full[s]
-      ws_mbar_init(bars + WS_SLOTS + s, 32 * 8);                 // empty[s]: the 8 passes of a chunk x 32 lanes
+      ws_mbar_init(bars + WS_SLOTS + s, 32 * 8);                 // empty[s]: the 8 pass slots of a chunk x 32 lanes
     }
     ws_mbar_init(bars + 2 * WS_SLOTS, 1);                        // xfull: TMA transaction barrier of the input chunk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the R warps start the input of chunk 0 before anything else: it then arrives while the tables are staged and the
-  // taps are loaded (chunk 0 of a clip starts in the zero padding, so it normally takes the cp.async edge path)
-  int pre_sh = -1;
-  bool pre_tma = false;
-  if (warp < WS_R_WARPS && n_chunks > 0) {
-    const int mode0 = fp.ws_mode[p.rate_id ? p.rate_id[b] : 0];
-    const int nh0 = last_hop + 1 > 32 ? 32 : last_hop + 1;
-    int64_t lo0 = 0;
-    int nx0 = 0;
-    if (mode0 == 1) { lo0 = (int64_t)row_begin * FK_ORIG - FK_WIDTH; nx0 = (nh0 - 1) * FK_ORIG + FK_KLEN + 8; }
-    else if (MULTI && mode0 == 2) { lo0 = (int64_t)row_begin * (3 * FK_SHIFT) - WS_W48; nx0 = (nh0 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8; }
-    else if (MULTI && mode0 == 3) { lo0 = (int64_t)(row_begin >> 1) * FK_ORIG - WS_W22; nx0 = (((nh0 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8; }
-    if (nx0 > 0) {
-      pre_sh = ws_shift(c.wav + lo0);
-      pre_tma = lo0 >= 4 && lo0 + nx0 + 4 <= c.n_in;
-      if (pre_tma) {
-        if (tid == 0) ws_tma_load(xbuf, c.wav + lo0 - pre_sh, (unsigned)(((nx0 + pre_sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
-      } else {
-        ws_load_edge_issue(c, lo0, nx0, pre_sh, xbuf, tid);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-    }
-  }
-  if (n_real_pass > 0) {
-    for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
-    for (int i = tid; i < fp.mel_rows * 32; i += WS_THREADS) smelw[i] = __ldg(fp.melw + i);
-  }
-  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
-  if (!STATS && p.masks) {
-    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
-    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
-  }
-  // lane constants: one copy per CTA (= per clip); 29 rows x 32 lanes spread over all threads so the dependent
-  // global loads of the set-up overlap
-  for (int e = tid; e < FK_LANE_ROWS * 32; e += WS_THREADS) {
+  for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
+  for (int i = tid; i < fp.mel_rows * 32; i += WS_THREADS) smelw[i] = __ldg(fp.melw + i);
+  // static lane constants, one copy per CTA: rows 0..12 window, 13..16 first FFT bin of the slot, 17..20 output offset of
+  // its mel bin, 21..24 the mel bin itself (the per-clip epilogue constants are folded from it by each F warp)
+  for (int e = tid; e < 25 * 32; e += WS_THREADS) {
     const int row = e >> 5, ln = e & 31;
     float v;
     if (row < 13) {
       v = (ln + 32 * row < FK_SIZE) ? __ldg(p.window + ln + 32 * row) : 0.f;
     } else {
-      const int i = (row - 13) & 3, kind = (row - 13) >> 2;      // kind 0 mstart, 1 mbin, 2 scale, 3 shift
+      const int i = (row - 13) & 3, kind = (row - 13) >> 2;      // kind 0 mstart, 1 output offset, 2 mel bin
       const bool have = i < fp.mel_groups;
       const int m = have ? __ldg(fp.mel_slot_bin + ln + 32 * i) : p.n_mel;
-      float sc, shf;
-      fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, sc, shf);   // frequency mask: the whole column is 0.0
       if (kind == 0) v = __int_as_float(have ? __ldg(fp.mel_slot_start + ln + 32 * i) : 0);
       else if (kind == 1) v = __int_as_float(m < p.n_mel ? m * ((STATS || p.layout == 0) ? 1 : p.out_frames) : -1);
-      else if (kind == 2) v = sc;
-      else v = shf;
+      else v = __int_as_float(m);
     }
     slane[e] = v;
   }
   __syncthreads();
 
-  // register reallocation is per warpgroup: warpgroup 0 (both R warps and F warps 0-1) grows to 232, the rest shrink
-  // R warps are warpgroup 0 (putting them last, where the issue arbiter would favour them, measured 3% slower:
-  // the pipeline is balanced and latency-bound, not R-bound)
+  // register reallocation is per warpgroup: warpgroup 0 (the R warps) grows to 232, the F warpgroups shrink to 136
+  // (R warps last, where the issue arbiter would favour them, measured 3% slower)
   const bool is_r = warp < WS_R_WARPS;
   if (is_r) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
@@ -250,278 +236,247 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     // =============================== R warps: resampler ==========================================
     // mode 1: 441 -> 160 (44.1 kHz), 2: 3 -> 1 (48 kHz), 3: 441 -> 320 (22.05 kHz): register-resident taps, one TMA
     // bulk copy per chunk; mode 0: any other ratio (per-sample loop) or no resampling at all
-    const int rid = p.rate_id ? p.rate_id[b] : 0;
-    const int mode = fp.ws_mode[rid];
     const int rt = tid;                                          // 0..127
     const int rw = warp;                                         // R warp index
     const int g = lane;
     unsigned x_parity = 0;
-    // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy
-    auto stage_x = [&](int64_t in_lo, int nx) -> int {
-      if (pre_sh >= 0) {                                          // chunk 0: issued at the top of the kernel
-        const int sh0 = pre_sh;
-        pre_sh = -1;
-        if (pre_tma) {
-          ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
-          x_parity ^= 1u;
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          ws_bar_r();
-        }
-        return sh0;
-      }
-      const float* gsrc = c.wav + in_lo;
-      const int sh = ws_shift(gsrc);
-      if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
-        if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
-        ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
-        x_parity ^= 1u;
-      } else {
-        ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
-        ws_bar_r();
-      }
-      return sh;
-    };
-    // warm the L2 with the NEXT chunk's input while this one is being resampled: the xbuf itself cannot be loaded ahead
-    // (every lane visits every hop of the chunk), but a bulk L2 prefetch takes the DRAM latency out of the next TMA copy
-    auto prefetch_x = [&](int64_t in_lo, int nx) {
-      if (rt == 32 && in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
-        const float* gsrc = c.wav + in_lo;
-        const int sh = ws_shift(gsrc);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc - sh), "r"((unsigned)(((nx + sh + 3) >> 2) << 4)) : "memory");
-      }
-    };
-    auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {
-      float* o = rb + q * FK_SHIFT + FK_RP * g;
+    // the taps of the current mode (pairs): mode 1 T[r][jj] = TT[18 r + jj]; mode 2 He[i] = TT[i], Ho[i] = TT[21 + i];
+    // mode 3 T[r][i] = TT[10 r + i].  Reloaded only when the rate of the next clip differs.
+    unsigned long long TT[FK_RP * WS_LT / 2];
 #pragma unroll
-      for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
-      if (slot == 0 && q < WS_MIRROR) {
-        float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
+    for (int i = 0; i < FK_RP * WS_LT / 2; ++i) TT[i] = 0ull;
+    int cur_mode = -1, k0 = 0, skew = 0;
+    if (!MULTI) {                                                // single tuned rate: its taps are loaded once per CTA
+      const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
 #pragma unroll
-        for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
-      }
-    };
+      for (int i = 0; i < FK_RP * WS_LT / 2; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
+      k0 = __ldg(fp.ws_k0g + g);
+      skew = ((g - k0) * 9) & 31;
+    }
+    int gch = 0;                                                 // chunks this CTA has produced so far
 #ifdef B200_WS_TIMING
     long long tc_ = 0;
 #endif
-    // ---------------- 441 -> 160: lane = 5 phases, 180 taps in registers, hop rotation (see the header) ----------
-    // (T, k0, skew live at branch scope: ptxas schedules the hop loop 1-2 % better than with block-local ones)
-    unsigned long long T[FK_RP][WS_LT / 2];
-    int k0 = 0, skew = 0;
-    if (mode == 1) {
-      const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
+    for (int item = blockIdx.x; item < total; item += stride) {
+      const int b = item / fp.segs;
+      const ClipInfo c = clip_info(p, b);
+      const WsItem it = ws_item<STATS>(p, fp, c, item);
+      if (!it.valid) continue;
+      if (!STATS && it.seg == 0 && tid == 0 && p.n_frames_out) p.n_frames_out[b] = it.m_eff;
+      if (it.n_chunks == 0) continue;
+      const int rid = p.rate_id ? p.rate_id[b] : 0;
+      const int mode = fp.ws_mode[rid];
+      const int row_begin = it.row_begin, last_hop = it.last_hop, n_chunks = it.n_chunks;
+      if (MULTI && mode != cur_mode) {
+        cur_mode = mode;
+        if (mode == 1) {
+          const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
 #pragma unroll
-      for (int r = 0; r < FK_RP; ++r)
+          for (int i = 0; i < FK_RP * WS_LT / 2; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
+          k0 = __ldg(fp.ws_k0g + g);
+          skew = ((g - k0) * 9) & 31;
+        } else if (MULTI && mode == 2) {
+          const float2* tp = reinterpret_cast<const float2*>(fp.ws_t48);
 #pragma unroll
-        for (int jj = 0; jj < WS_LT / 2; ++jj) {
-          const float2 t2 = __ldg(tp + r * (WS_LT / 2) + jj);
-          T[r][jj] = ws_pack(t2.x, t2.y);
+          for (int i = 0; i < 2 * WS_P48; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
+        } else if (MULTI && mode == 3) {
+          const int par = rw & 1;
+          const float2* tp = reinterpret_cast<const float2*>(fp.ws_t22 + (size_t)(par * 32 + g) * (FK_RP * WS_LT22));
+#pragma unroll
+          for (int i = 0; i < FK_RP * WS_LT22 / 2; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
+          k0 = __ldg(fp.ws_k22 + par * 32 + g);
         }
-      k0 = __ldg(fp.ws_k0g + g);
-      skew = ((g - k0) * 9) & 31;
-    } else {
-#pragma unroll
-      for (int r = 0; r < FK_RP; ++r)
-#pragma unroll
-        for (int jj = 0; jj < WS_LT / 2; ++jj) T[r][jj] = 0ull;
-    }
-    if (mode == 1) {
-      for (int ch = 0; ch < n_chunks; ++ch) {                    // [phase: ws_resample_loop]
-        const int slot = ch % WS_SLOTS;
-        float* rb = ring + slot * 32 * FK_SHIFT;
-        int nh = last_hop - 32 * ch + 1;                         // hops of this chunk anyone reads
-        nh = nh > 32 ? 32 : nh;
-        const int64_t hop0 = (int64_t)row_begin + 32 * ch;       // absolute hop (= 16 kHz sample / 160) of ring row 0 of the slot
-#ifdef B200_WS_TIMING
-        const long long ta_ = clock64();
-#endif
-        if (ch + 1 < n_chunks) {
-          int nh2 = last_hop - 32 * (ch + 1) + 1;
-          nh2 = nh2 > 32 ? 32 : nh2;
-          prefetch_x((hop0 + 32) * FK_ORIG - FK_WIDTH, (nh2 - 1) * FK_ORIG + FK_KLEN + 8);
+      }
+      // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy
+      auto stage_x = [&](int64_t in_lo, int nx) -> int {
+        const float* gsrc = c.wav + in_lo;
+        const int sh = ws_shift(gsrc);
+        if (in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
+          if (rt == 0) ws_tma_load(xbuf, gsrc - sh, (unsigned)(((nx + sh + 3) >> 2) << 4), bars + 2 * WS_SLOTS);
+          ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
+          x_parity ^= 1u;
+        } else {
+          ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+          ws_bar_r();
         }
-        const int sh = stage_x(hop0 * FK_ORIG - FK_WIDTH, (nh - 1) * FK_ORIG + FK_KLEN + 8);
+        return sh;
+      };
+      // warm the L2 with the NEXT chunk's input while this one is being resampled: the xbuf itself cannot be loaded ahead
+      // (every lane visits every hop of the chunk), but a bulk L2 prefetch takes the DRAM latency out of the next TMA copy
+      auto prefetch_x = [&](int64_t in_lo, int nx) {
+        if (rt == 32 && in_lo >= 4 && in_lo + nx + 4 <= c.n_in) {
+          const float* gsrc = c.wav + in_lo;
+          const int sh = ws_shift(gsrc);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc - sh), "r"((unsigned)(((nx + sh + 3) >> 2) << 4)) : "memory");
+        }
+      };
+      auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {
+        float* o = rb + q * FK_SHIFT + FK_RP * g;
+#pragma unroll
+        for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
+        if (slot == 0 && q < WS_MIRROR) {
+          float* om = ring + (WS_RING_ROWS + q) * FK_SHIFT + FK_RP * g;
+#pragma unroll
+          for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
+        }
+      };
+      // one loop per mode (not one loop with the mode switch inside): only the state of the running mode stays live in
+      // registers, which is what lets ptxas issue the input loads of a hop well ahead of the FFMA2 chain
+      auto run_chunks = [&](auto&& chunk_body) {
+        for (int ch = 0; ch < n_chunks; ++ch) {                  // [phase: ws_resample_loop]
+          const int gc = gch + ch;                               // chunk number of this CTA: ring slot and barrier phase
+          const int slot = gc % WS_SLOTS;
+          float* rb = ring + slot * 32 * FK_SHIFT;
+          int nh = last_hop - 32 * ch + 1;                       // hops of this chunk anyone reads
+          nh = nh > 32 ? 32 : nh;
+          int nh2 = last_hop - 32 * (ch + 1) + 1;                // ... and of the next one (0: none)
+          nh2 = ch + 1 < n_chunks ? (nh2 > 32 ? 32 : nh2) : 0;
+          const int64_t hop0 = (int64_t)row_begin + 32 * ch;     // absolute hop (= 16 kHz sample / 160) of ring row 0 of the slot
+          chunk_body(gc, slot, rb, nh, nh2, hop0);
+          ws_mbar_arrive(bars + slot);                           // full[slot]: release the 32 hops to the F warps
+          ws_bar_r();                                            // everyone is done with xbuf before the next load
+        }
+      };
+      if (mode == 1) {
+        run_chunks([&](int gc, int slot, float* rb, int nh, int nh2, int64_t hop0) {
+          // ------------ 441 -> 160: lane = 5 phases, 180 taps in registers, hop rotation (see the header) ------------
 #ifdef B200_WS_TIMING
-        const long long tb_ = clock64();
-        WS_TACC(0, ta_);
+          const long long ta_ = clock64();
 #endif
-        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
+          if (nh2 > 0) prefetch_x((hop0 + 32) * FK_ORIG - FK_WIDTH, (nh2 - 1) * FK_ORIG + FK_KLEN + 8);
+          const int sh = stage_x(hop0 * FK_ORIG - FK_WIDTH, (nh - 1) * FK_ORIG + FK_KLEN + 8);
 #ifdef B200_WS_TIMING
-        tc_ = clock64();
-        WS_TACC(1, tb_);
+          const long long tb_ = clock64();
+          WS_TACC(0, ta_);
 #endif
-        const float* xs = xbuf + sh + k0;
-        if (nh > 8) {
+          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
+#ifdef B200_WS_TIMING
+          tc_ = clock64();
+          WS_TACC(1, tb_);
+#endif
+          const float* xs = xbuf + sh + k0;
+          if (nh > 8) {
 #pragma unroll 1
-          for (int i = 0; i < WS_R_ITERS; ++i) {
-            const int q = (WS_R_ITERS * rw + i + skew) & 31;
-            float y[FK_RP];
-            ws_resample_hop(xs + q * FK_ORIG, T, y);
-            put_hop(rb, slot, q, y);
+            for (int i = 0; i < WS_R_ITERS; ++i) {
+              const int q = (WS_R_ITERS * rw + i + skew) & 31;
+              float y[FK_RP];
+              ws_resample_hop(xs + q * FK_ORIG, TT, y);
+              put_hop(rb, slot, q, y);
+            }
+          } else {                                               // short tail chunk: hop = warp, warp + 4
+#pragma unroll 1
+            for (int q = rw; q < nh; q += WS_R_WARPS) {
+              float y[FK_RP];
+              ws_resample_hop(xs + q * FK_ORIG, TT, y);
+              put_hop(rb, slot, q, y);
+            }
           }
-        } else {                                                 // short tail chunk: hop = warp, warp + 4
+#ifdef B200_WS_TIMING
+          WS_TACC(2, tc_); if (lane == 0) atomicAdd(&g_ws_timing[3], 1ull);
+#endif
+        });
+      } else if (MULTI && mode == 2) {
+        run_chunks([&](int gc, int slot, float* rb, int nh, int nh2, int64_t hop0) {
+          // ------------ 3 -> 1 (48 kHz): ONE phase of 41 taps shared by every lane; lane = outputs 5g..5g+4 of a hop, whose
+          // windows start 3 samples apart: even starts pair the taps as (h[2i], h[2i+1]) = He, odd starts as (h[2i-1], h[2i])
+          // = Ho.  Lanes read x at stride 15 (odd): conflict free without any rotation.       // [phase: ws_resample_48k]
+          if (nh2 > 0) prefetch_x((hop0 + 32) * (3 * FK_SHIFT) - WS_W48, (nh2 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
+          const int sh = stage_x(hop0 * (3 * FK_SHIFT) - WS_W48, (nh * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
+          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
+          const float* xs = xbuf + sh + 3 * FK_RP * g;
 #pragma unroll 1
           for (int q = rw; q < nh; q += WS_R_WARPS) {
+            const float* xq = xs + q * (3 * FK_SHIFT);
+            unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int j = 0; j < WS_P48 + 6; ++j) {               // x pairs (2j, 2j+1); phase r starts at pair {0,1,3,4,6}[r]
+              const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
+              if (j < WS_P48) acc[0] = ws_fma2(xp, TT[j], acc[0]);
+              if (j >= 1 && j < WS_P48 + 1) acc[1] = ws_fma2(xp, TT[WS_P48 + j - 1], acc[1]);
+              if (j >= 3 && j < WS_P48 + 3) acc[2] = ws_fma2(xp, TT[j - 3], acc[2]);
+              if (j >= 4 && j < WS_P48 + 4) acc[3] = ws_fma2(xp, TT[WS_P48 + j - 4], acc[3]);
+              if (j >= 6) acc[4] = ws_fma2(xp, TT[j - 6], acc[4]);
+            }
             float y[FK_RP];
-            ws_resample_hop(xs + q * FK_ORIG, T, y);
+#pragma unroll
+            for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
             put_hop(rb, slot, q, y);
           }
-        }
-#ifdef B200_WS_TIMING
-        WS_TACC(2, tc_); if (lane == 0) atomicAdd(&g_ws_timing[3], 1ull);
-#endif
-        ws_mbar_arrive(bars + slot);                             // full[slot]: release the 32 hops to the F warps
-        ws_bar_r();                                              // everyone is done with xbuf before the next load
-      }
-    } else if (MULTI && mode == 2) {
-      // ---------------- 3 -> 1 (48 kHz): ONE phase of 41 taps shared by every lane; lane = outputs 5g..5g+4 of a hop,
-      // whose windows start 3 samples apart: even starts pair the taps as (h[2i], h[2i+1]), odd starts as (h[2i-1], h[2i]).
-      // Lanes read x at stride 15 (odd): conflict free without any rotation.                 // [phase: ws_resample_48k]
-      unsigned long long He[WS_P48], Ho[WS_P48];
-      {
-        const float2* tp = reinterpret_cast<const float2*>(fp.ws_t48);
-#pragma unroll
-        for (int i = 0; i < WS_P48; ++i) {
-          const float2 e = __ldg(tp + i), o = __ldg(tp + WS_P48 + i);
-          He[i] = ws_pack(e.x, e.y); Ho[i] = ws_pack(o.x, o.y);
-        }
-      }
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int slot = ch % WS_SLOTS;
-        float* rb = ring + slot * 32 * FK_SHIFT;
-        int nh = last_hop - 32 * ch + 1;
-        nh = nh > 32 ? 32 : nh;
-        const int64_t hop0 = (int64_t)row_begin + 32 * ch;
-        if (ch + 1 < n_chunks) {
-          int nh2 = last_hop - 32 * (ch + 1) + 1;
-          nh2 = nh2 > 32 ? 32 : nh2;
-          prefetch_x((hop0 + 32) * (3 * FK_SHIFT) - WS_W48, (nh2 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
-        }
-        const int sh = stage_x(hop0 * (3 * FK_SHIFT) - WS_W48, (nh * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
-        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
-        const float* xs = xbuf + sh + 3 * FK_RP * g;
+        });
+      } else if (MULTI && mode == 3) {
+        run_chunks([&](int gc, int slot, float* rb, int nh, int nh2, int64_t hop0) {
+          // ------------ 441 -> 320 (22.05 kHz): 320 phases = two hops; even R warps hold the taps of phases 0..159 (even
+          // hops), odd R warps those of 160..319; lane = 5 phases x 20 taps.  The host picks each lane's window start inside
+          // its slack so that the 32 starts are distinct mod 32: conflict free without rotation.  // [phase: ws_resample_22k]
+          const int par = rw & 1;
+          const int np = (nh + 1) >> 1;                          // periods (pairs of hops) of this chunk; hop0 is even
+          if (nh2 > 0) prefetch_x(((hop0 >> 1) + 16) * FK_ORIG - WS_W22, (((nh2 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
+          const int sh = stage_x((hop0 >> 1) * FK_ORIG - WS_W22, (np - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
+          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
+          const float* xs = xbuf + sh + k0;
 #pragma unroll 1
-        for (int q = rw; q < nh; q += WS_R_WARPS) {
-          const float* xq = xs + q * (3 * FK_SHIFT);
-          unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+          for (int Q = rw >> 1; 2 * Q + par < nh; Q += WS_R_WARPS / 2) {
+            const float* xq = xs + Q * FK_ORIG;
+            unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-          for (int j = 0; j < WS_P48 + 6; ++j) {                 // x pairs (2j, 2j+1); phase r starts at pair {0,1,3,4,6}[r]
-            const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
-            if (j < WS_P48) acc[0] = ws_fma2(xp, He[j], acc[0]);
-            if (j >= 1 && j < WS_P48 + 1) acc[1] = ws_fma2(xp, Ho[j - 1], acc[1]);
-            if (j >= 3 && j < WS_P48 + 3) acc[2] = ws_fma2(xp, He[j - 3], acc[2]);
-            if (j >= 4 && j < WS_P48 + 4) acc[3] = ws_fma2(xp, Ho[j - 4], acc[3]);
-            if (j >= 6) acc[4] = ws_fma2(xp, He[j - 6], acc[4]);
+            for (int j = 0; j < WS_LT22 / 2 + 2; ++j) {          // phase r starts at pair ws_off22(r) / 2
+              const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
+#pragma unroll
+              for (int r = 0; r < FK_RP; ++r) {
+                const int i = j - ws_off22(r) / 2;
+                if (i >= 0 && i < WS_LT22 / 2) acc[r] = ws_fma2(xp, TT[r * (WS_LT22 / 2) + i], acc[r]);
+              }
+            }
+            float y[FK_RP];
+#pragma unroll
+            for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
+            put_hop(rb, slot, 2 * Q + par, y);
           }
-          float y[FK_RP];
-#pragma unroll
-          for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
-          put_hop(rb, slot, q, y);
-        }
-        ws_mbar_arrive(bars + slot);
-        ws_bar_r();
-      }
-    } else if (MULTI && mode == 3) {
-      // ---------------- 441 -> 320 (22.05 kHz): 320 phases = two hops; even R warps hold the taps of phases 0..159 (even
-      // hops), odd R warps those of 160..319; lane = 5 phases x 20 taps.  The host picks each lane's window start inside
-      // its slack so that the 32 starts are distinct mod 32: conflict free without rotation.   // [phase: ws_resample_22k]
-      const int par = rw & 1;
-      unsigned long long T[FK_RP][WS_LT22 / 2];
-      {
-        const float2* tp = reinterpret_cast<const float2*>(fp.ws_t22 + (size_t)(par * 32 + g) * (FK_RP * WS_LT22));
-#pragma unroll
-        for (int r = 0; r < FK_RP; ++r)
-#pragma unroll
-          for (int jj = 0; jj < WS_LT22 / 2; ++jj) {
-            const float2 t2 = __ldg(tp + r * (WS_LT22 / 2) + jj);
-            T[r][jj] = ws_pack(t2.x, t2.y);
-          }
-      }
-      const int k0 = __ldg(fp.ws_k22 + par * 32 + g);
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int slot = ch % WS_SLOTS;
-        float* rb = ring + slot * 32 * FK_SHIFT;
-        int nh = last_hop - 32 * ch + 1;
-        nh = nh > 32 ? 32 : nh;
-        const int64_t hop0 = (int64_t)row_begin + 32 * ch;       // even: segments start on multiples of 32 frames
-        const int np = (nh + 1) >> 1;                            // periods (pairs of hops) of this chunk
-        if (ch + 1 < n_chunks) {
-          int nh2 = last_hop - 32 * (ch + 1) + 1;
-          nh2 = nh2 > 32 ? 32 : nh2;
-          prefetch_x(((hop0 >> 1) + 16) * FK_ORIG - WS_W22, (((nh2 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
-        }
-        const int sh = stage_x((hop0 >> 1) * FK_ORIG - WS_W22, (np - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
-        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
-        const float* xs = xbuf + sh + k0;
-#pragma unroll 1
-        for (int Q = rw >> 1; 2 * Q + par < nh; Q += WS_R_WARPS / 2) {
-          const float* xq = xs + Q * FK_ORIG;
-          unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
-#pragma unroll
-          for (int j = 0; j < WS_LT22 / 2 + 2; ++j) {            // phase r starts at pair ws_off22(r) / 2
-            const unsigned long long xp = ws_pack(xq[2 * j], xq[2 * j + 1]);
-#pragma unroll
-            for (int r = 0; r < FK_RP; ++r) {
-              const int i = j - ws_off22(r) / 2;
-              if (i >= 0 && i < WS_LT22 / 2) acc[r] = ws_fma2(xp, T[r][i], acc[r]);
+        });
+      } else {
+        run_chunks([&](int gc, int slot, float* rb, int nh, int nh2, int64_t hop0) {
+          (void)nh2;
+          // ------------ other rates: per-sample polyphase loop (or plain copy) into the same ring slot ------------
+          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
+          const int total_s = nh * FK_SHIFT;
+          const int64_t s_base = hop0 * FK_SHIFT;                // absolute resampled index of slot row 0
+          if (c.R.identity) {
+            for (int t = rt; t < total_s; t += WS_R_THREADS) {
+              const int64_t s2 = s_base + t;
+              const float v = (s2 < c.n_in) ? __ldg(c.wav + s2) : 0.f;
+              rb[t] = v;
+              if (slot == 0 && t < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + t] = v;
+            }
+          } else {
+            const int part = fp.gen_part[rid];
+            for (int done = 0; done < total_s; done += part) {
+              const int cnt = (total_s - done < part) ? total_s - done : part;
+              const int64_t s0 = s_base + done;
+              const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
+              const int64_t in_lo = q_lo * c.R.orig - c.R.width;
+              const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
+              if (done > 0) ws_bar_r();
+              const int sh = ws_shift(c.wav + in_lo);
+              ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+              ws_bar_r();
+              const float* xsg = xbuf + sh;
+              for (int t = rt; t < cnt; t += WS_R_THREADS) {
+                const int64_t s2 = s0 + t;
+                const int64_t q = s2 / c.R.nw;
+                const int ph = (int)(s2 - q * c.R.nw);
+                const float* tpp = c.R.taps + (size_t)ph * c.R.L;
+                const float* x = xsg + (q * c.R.orig + __ldg(c.R.k0 + ph) - c.R.width - in_lo);
+                float acc = 0.f;
+                for (int j = 0; j < c.R.L; ++j) acc = fmaf(__ldg(tpp + j), x[j], acc);
+                const int rel = done + t;
+                rb[rel] = acc;
+                if (slot == 0 && rel < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + rel] = acc;
+              }
             }
           }
-          float y[FK_RP];
-#pragma unroll
-          for (int r = 0; r < FK_RP; ++r) y[r] = __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
-          put_hop(rb, slot, 2 * Q + par, y);
-        }
-        ws_mbar_arrive(bars + slot);
-        ws_bar_r();
+        });
       }
-    } else {
-      // ---------------- other rates: per-sample polyphase loop (or plain copy) into the same ring slot ----------------
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int slot = ch % WS_SLOTS;
-        float* rb = ring + slot * 32 * FK_SHIFT;
-        int nh = last_hop - 32 * ch + 1;
-        nh = nh > 32 ? 32 : nh;
-        const int64_t hop0 = (int64_t)row_begin + 32 * ch;
-        if (ch >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((ch / WS_SLOTS - 1) & 1));
-        const int total = nh * FK_SHIFT;
-        const int64_t s_base = hop0 * FK_SHIFT;                  // absolute resampled index of slot row 0
-        if (c.R.identity) {
-          for (int t = rt; t < total; t += WS_R_THREADS) {
-            const int64_t s = s_base + t;
-            const float v = (s < c.n_in) ? __ldg(c.wav + s) : 0.f;
-            rb[t] = v;
-            if (slot == 0 && t < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + t] = v;
-          }
-        } else {
-          const int part = fp.gen_part[rid];
-          for (int done = 0; done < total; done += part) {
-            const int cnt = (total - done < part) ? total - done : part;
-            const int64_t s0 = s_base + done;
-            const int64_t q_lo = s0 / c.R.nw, q_hi = (s0 + cnt - 1) / c.R.nw;
-            const int64_t in_lo = q_lo * c.R.orig - c.R.width;
-            const int nx = (int)((q_hi - q_lo) * c.R.orig + c.R.klen);
-            if (done > 0) ws_bar_r();
-            const int sh = ws_shift(c.wav + in_lo);
-            ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
-            ws_bar_r();
-            const float* xsg = xbuf + sh;
-            for (int t = rt; t < cnt; t += WS_R_THREADS) {
-              const int64_t s = s0 + t;
-              const int64_t q = s / c.R.nw;
-              const int ph = (int)(s - q * c.R.nw);
-              const float* tpp = c.R.taps + (size_t)ph * c.R.L;
-              const float* x = xsg + (q * c.R.orig + __ldg(c.R.k0 + ph) - c.R.width - in_lo);
-              float acc = 0.f;
-              for (int j = 0; j < c.R.L; ++j) acc = fmaf(__ldg(tpp + j), x[j], acc);
-              const int rel = done + t;
-              rb[rel] = acc;
-              if (slot == 0 && rel < WS_MIRROR * FK_SHIFT) ring[WS_RING_ROWS * FK_SHIFT + rel] = acc;
-            }
-          }
-        }
-        ws_mbar_arrive(bars + slot);                             // full[slot]: release the 32 hops to the F warps
-        ws_bar_r();                                              // everyone is done with xbuf before the next load
-      }
+      gch += n_chunks;
     }
   } else {
     // =============================== F warps: frames =============================================
@@ -532,32 +487,58 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       L.mstart[i] = __float_as_int(slane[(13 + i) * 32 + lane]); L.mbin[i] = __float_as_int(slane[(17 + i) * 32 + lane]);
-      L.nscale[i] = slane[(21 + i) * 32 + lane]; L.nshift[i] = slane[(25 + i) * 32 + lane];
+      L.nscale[i] = 1.f; L.nshift[i] = 0.f;
     }
     double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_ss[4] = {0.0, 0.0, 0.0, 0.0};
+    long long st_n = 0;
     float* Ebuf = ebuf + wf * FK_EBUF;
-    for (int pp = wf; pp < n_pass; pp += WS_F_WARPS) {           // [phase: ws_frame_loop]
-      const int t0 = row_begin + 4 * pp;
-      int n_live = m_eff - t0;
-      n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
-#ifdef B200_WS_TIMING
-      const long long tf0_ = clock64();
-#endif
-      if (n_live > 0) {
-        const int chn = (4 * pp + 5) >> 5;                       // newest chunk this pass reads
-        ws_mbar_wait(bars + chn % WS_SLOTS, (unsigned)((chn / WS_SLOTS) & 1));
+    int gch = 0;                                                 // chunks / pass slots of the items this CTA has finished
+    unsigned gpp = 0;
+    for (int item = blockIdx.x; item < total; item += stride) {
+      const int b = item / fp.segs;
+      const ClipInfo c = clip_info(p, b);
+      const WsItem it = ws_item<STATS>(p, fp, c, item);
+      if (!it.valid) continue;
+      int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+      if (!STATS && p.masks) {
+        mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+        mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
       }
+      // per-clip epilogue constants: normalisation folded with ln 2, frequency mask = zero scale and shift
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = __float_as_int(slane[(21 + i) * 32 + lane]);
+        fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, L.nscale[i], L.nshift[i]);
+      }
+      const int row0 = (gch % WS_SLOTS) * 32;                    // ring row of the item's first hop
+      for (int pp = (int)((wf - gpp) & (WS_F_WARPS - 1)); pp < it.pp_total; pp += WS_F_WARPS) {   // [phase: ws_frame_loop]
+        if (pp < it.n_pass) {
+          const int t0 = it.row_begin + 4 * pp;
+          int n_live = it.m_eff - t0;
+          n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
 #ifdef B200_WS_TIMING
-      const long long tf1_ = clock64();
-      WS_TACC(4, tf0_);
+          const long long tf0_ = clock64();
 #endif
-      const int row = (4 * pp) % WS_RING_ROWS;
-      fk_frame_pass<STATS, AST, FK_SHIFT, FkLane>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, row_end, lane,
-                                          mk0, mk1, mk2, mk3, st_s, st_ss);
+          if (n_live > 0) {
+            const int gc = gch + ((4 * pp + 5) >> 5);            // newest chunk this pass reads
+            ws_mbar_wait(bars + gc % WS_SLOTS, (unsigned)((gc / WS_SLOTS) & 1));
+          }
 #ifdef B200_WS_TIMING
-      WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);
+          const long long tf1_ = clock64();
+          WS_TACC(4, tf0_);
 #endif
-      if (pp < 8 * n_chunks) ws_mbar_arrive(bars + WS_SLOTS + (pp >> 3) % WS_SLOTS);   // empty[slot of the pass's own rows]
+          const int row = (row0 + 4 * pp) % WS_RING_ROWS;
+          fk_frame_pass<STATS, AST, FK_SHIFT, FkLane>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, it.row_end, lane,
+                                              mk0, mk1, mk2, mk3, st_s, st_ss);
+#ifdef B200_WS_TIMING
+          WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);
+#endif
+        }
+        if (pp < 8 * it.n_chunks) ws_mbar_arrive(bars + WS_SLOTS + (gch + (pp >> 3)) % WS_SLOTS);   // empty[slot of the pass's own rows]
+      }
+      if (STATS && wf == 0) st_n += it.n_real;
+      gch += it.n_chunks;
+      gpp += (unsigned)it.pp_total;
     }
     if (STATS) {
 #pragma unroll
@@ -568,7 +549,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           atomicAdd(p.sums + p.n_cols + m, st_ss[i]);
         }
       }
-      if (wf == 0 && lane == 0 && n_real > 0) atomicAdd(p.sums + 2 * p.n_cols, (double)n_real);
+      if (wf == 0 && lane == 0 && st_n > 0) atomicAdd(p.sums + 2 * p.n_cols, (double)st_n);
     }
   }
 }
