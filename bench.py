@@ -40,10 +40,10 @@ FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 def measured_traffic():
     """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ws_full_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    (profiles/r01c_ws_full_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
     try:
         tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r01_ws_full_metrics.csv")):
+        for line in open(os.path.join(ROOT, "profiles", "r01c_ws_full_metrics.csv")):
             f = line.strip().split(",")
             if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
