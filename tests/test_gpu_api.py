@@ -264,3 +264,42 @@ def test_reference_actual_batch_and_masks(b2, O):
     mine = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, frontend="melspectrogram",
                                                      normalize=False)).preprocess(w, 44100)
     assert np.abs(mine.numpy() - db.numpy()).max() < 5e-3
+
+
+@pytest.mark.parametrize("rate,seconds,frames", [(44100, 2.3, 1024), (48000, 1.1, 256), (22050, 0.9, 128), (16000, 1.5, 512)])
+def test_persistent_launch_is_bit_identical_to_one_cta_per_item(b2, O, monkeypatch, rate, seconds, frames):
+    """Dense batches larger than one wave run as ONE CTA per SM that walks its items with the resampler / frame pipeline
+    carried across clip (and segment) boundaries; B200FBANK_PERSIST=0 forces one CTA per item.  Same arithmetic per
+    item either way: features, frame counts and masks must be bit-identical, and match the oracle."""
+    B = 333                                            # > 2 waves of 148; 1024-frame outputs are split into segments
+    n = int(rate * seconds) + 5
+    g = torch.Generator().manual_seed(rate + frames)
+    wav = (torch.rand((B, n), generator=g) * 2 - 1).cuda()
+    table = (22050, 44100, 48000, 16000)
+    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    rid = torch.full((B,), table.index(rate), dtype=torch.int32)
+    random.seed(5)
+    masks = b2.specaugment.draw_masks(B, frames, 128, 48, 24, variant="reference")
+    kw = dict(out_frames=frames, rate_ids=rid, masks=masks, mean=AST_MEAN, std=AST_STD)
+    monkeypatch.setenv("B200FBANK_PERSIST", "1")
+    out_p, nfr_p = fe(wav, **kw)
+    monkeypatch.setenv("B200FBANK_PERSIST", "0")
+    out_1, nfr_1 = fe(wav, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(nfr_p, nfr_1) and torch.equal(out_p, out_1)
+    monkeypatch.setenv("B200FBANK_PERSIST", "1")
+    raw, _ = fe(wav, out_frames=frames, rate_ids=rid)               # un-normalised, un-masked: the oracle's units
+    for i in (0, 147, 148, 332):
+        ref = O.kaldi_fbank(O.resample(wav[i].cpu().numpy(), rate, 16000), O.ast_fbank_options())
+        m = min(ref.shape[0], frames)
+        assert m == int(nfr_p[i])
+        assert_logmel_close(raw[i, :m].cpu().numpy(), ref[:m], LOGMEL_TOL, f"persistent clip {i} @ {rate}")
+    # the stats pass takes the same two launch forms (float64 atomics: equal up to summation order)
+    sums = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200FBANK_PERSIST", flag)
+        ds = b2.DatasetStats(fe, max_frames=frames)
+        ds.update(wav, rate_ids=rid)
+        sums.append(ds.sums.cpu().numpy())
+    assert sums[0][-1] == sums[1][-1] == float(nfr_p.sum().item())
+    np.testing.assert_allclose(sums[0], sums[1], rtol=1e-11, atol=1e-6)
