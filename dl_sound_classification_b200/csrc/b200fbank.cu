@@ -7,6 +7,7 @@
 #include "../../include/b200fbank.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdarg>
@@ -149,6 +150,7 @@ struct b200fbank_plan {
   // warp-specialised kernel (fbank_ws.cuh); shares FastParams
   bool ws_ok = false;
   size_t ws_smem = 0;
+  int* ws_counters = nullptr;   // kWsCounters zero-initialised ints: work counters of dynamic persistent launches (one per launch in flight)
 };
 
 namespace {
@@ -395,6 +397,8 @@ static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin
   }
 }
 
+constexpr int kWsCounters = 64;
+
 int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   using namespace b200;
   const b200fbank_opts& o = p->o;
@@ -606,10 +610,17 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     if (int rc = dev_copy(t48.data(), t48.size() * 4, (const void**)&f.ws_t48)) return rc;
     if (int rc = dev_copy(t22.data(), t22.size() * 4, (const void**)&f.ws_t22)) return rc;
     if (int rc = dev_copy(k22.data(), k22.size() * 4, (const void**)&f.ws_k22)) return rc;
-    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32) * 4 + 128;
+    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32) * 4 + 256;
     // rates without the 44.1 kHz structure still run through this kernel's per-sample path
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;
+    {
+      void* d = nullptr;
+      CUDA_TRY(cudaMalloc(&d, kWsCounters * sizeof(int)));
+      CUDA_TRY(cudaMemset(d, 0, kWsCounters * sizeof(int)));
+      owned.push_back(d);
+      p->ws_counters = (int*)d;
+    }
     f.ws_multi = 0;
     for (int i = 0; i < B200_MAX_RATES; ++i) f.ws_multi |= (f.ws_mode[i] >= 2);
 #define B200_WS_ATTR(S, A, M) CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<S, A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin))
@@ -706,7 +717,7 @@ int pick_seg_frames(const b200::FastParams& f, int B, int frames, int slots = 29
 // Persistent launch of the warp-specialised kernel: dense batches (equal clips) larger than one wave run as one CTA
 // per SM that walks its items with the R/F pipeline carried across clip boundaries; ragged batches keep one CTA per
 // item so the hardware scheduler balances the uneven clips.  B200FBANK_PERSIST=0/1 overrides.
-void ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastParams& f, int64_t& grid) {
+int ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastParams& f, int64_t& grid, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0, n = 0;
@@ -714,12 +725,19 @@ void ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastP
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     sms = n;
   }
-  (void)p;
   const char* env = getenv("B200FBANK_PERSIST");
-  bool persist = d_offsets == nullptr;
-  if (env) persist = atoi(env) != 0;
-  f.ws_persist = (persist && grid > sms) ? 1 : 0;
+  int mode = d_offsets == nullptr ? 1 : 2;           // dense: static stride; ragged: dynamic claims
+  if (env) mode = atoi(env);
+  if (mode == 2 && !p->ws_counters) mode = 0;
+  f.ws_persist = (mode != 0 && grid > sms) ? mode : 0;
+  f.ws_counter = nullptr;
   if (f.ws_persist) grid = sms;
+  if (f.ws_persist == 2) {
+    static std::atomic<unsigned> seq{0};
+    f.ws_counter = p->ws_counters + (seq.fetch_add(1) % kWsCounters);
+    CUDA_TRY(cudaMemsetAsync(f.ws_counter, 0, sizeof(int), st));
+  }
+  return 0;
 }
 
 int check_device_call(const b200fbank_plan* p, const void* wav, const int64_t* offsets, int64_t clip_samples, int B) {
@@ -842,7 +860,7 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
     f.segs = (out_frames + f.seg_frames - 1) / f.seg_frames;
     int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
-    ws_pick_grid(p, d_offsets, f, grid);
+    if (int rc = ws_pick_grid(p, d_offsets, f, grid, st)) return rc;
     if (f.ws_multi) {
       if (f.ast_bank) b200::fbank_ws_kernel<false, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
       else b200::fbank_ws_kernel<false, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
@@ -936,7 +954,7 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
     f.segs = (max_frames + f.seg_frames - 1) / f.seg_frames;
     int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments exceeds the grid limit");
-    ws_pick_grid(p, d_offsets, f, grid);
+    if (int rc = ws_pick_grid(p, d_offsets, f, grid, (cudaStream_t)stream)) return rc;
     if (f.ws_multi) {
       if (f.ast_bank) b200::fbank_ws_kernel<true, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
       else b200::fbank_ws_kernel<true, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);

@@ -73,7 +73,9 @@ struct FastParams {
   // ws_k22: [2][32] window starts)
   int ws_mode[B200_MAX_RATES];
   int ws_multi;           // some entry has mode >= 2: launch the MULTI instantiation
-  int ws_persist;         // per launch: 1 = grid of #SMs CTAs looping over the items (dense batches), 0 = one item per CTA
+  int ws_persist;         // per launch: 0 = one item per CTA; 1 = grid of #SMs CTAs striding over the items (dense batches);
+                          // 2 = the same with items claimed from ws_counter (ragged batches: uneven clips)
+  int* ws_counter;        // per launch: zeroed device counter of the dynamic form
   const float* ws_t48;
   const float* ws_t22;
   const int* ws_k22;

@@ -143,6 +143,12 @@ __device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, i
   fk_cp_async_wait_all();
 }
 
+constexpr int WS_QN = 8;                                      // depth of the item queue of the dynamic persistent form
+__device__ __forceinline__ int ws_claim(const FastParams& fp, int total) {
+  const int id = (int)gridDim.x + atomicAdd(fp.ws_counter, 1);
+  return id < total ? id : -1;
+}
+
 // Geometry of one work item = one segment of one clip (recomputed by each role from the item number).
 struct WsItem {
   int b, seg, row_begin, row_end, m_eff;
@@ -195,6 +201,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = p.B * fp.segs;
   const int stride = fp.ws_persist ? (int)gridDim.x : total;     // items of this CTA: blockIdx.x, + stride, ...
+  // ws_persist == 2 (ragged batches): items come from a global counter instead; R thread 0 claims them one ahead and
+  // hands them to everybody through a small shared-memory queue: sq[0..7] item ids (-1 = no more), sq[8] = number
+  // published, sq[16..23] = per F warp, the item step it has reached (so a queue slot is never overwritten early)
+  const bool dyn = fp.ws_persist == 2;
+  volatile int* sq = reinterpret_cast<volatile int*>(bars + 8);
 
   if (tid == 0) {
 #pragma unroll
@@ -204,6 +215,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     }
     ws_mbar_init(bars + 2 * WS_SLOTS, 1);                        // xfull: TMA transaction barrier of the input chunk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 24; ++i) sq[i] = 0;
   }
   for (int i = tid; i < 512; i += WS_THREADS) stw[i] = __ldg(fp.tw + i);
   for (int i = tid; i < fp.mel_rows * 32; i += WS_THREADS) smelw[i] = __ldg(fp.melw + i);
@@ -257,7 +270,37 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #ifdef B200_WS_TIMING
     long long tc_ = 0;
 #endif
-    for (int item = blockIdx.x; item < total; item += stride) {
+    int pend = -1;                                               // thread 0: the item after the next one, claimed early
+    if (dyn && rt == 0) {
+      sq[0] = (int)blockIdx.x;
+      __threadfence_block();
+      sq[8] = 1;
+      pend = ws_claim(fp, total);
+    }
+    for (int k = 0;; ++k) {
+      int item;
+      if (dyn) {
+        if (rt == 0) {                                           // publish item k + 1, start claiming item k + 2
+          if (k + 1 >= WS_QN) {
+            int lo;
+            do {
+              lo = sq[16];
+#pragma unroll
+              for (int w = 1; w < WS_F_WARPS; ++w) lo = min(lo, sq[16 + w]);
+            } while (lo < k + 2 - WS_QN);
+          }
+          sq[(k + 1) & (WS_QN - 1)] = pend;
+          __threadfence_block();
+          sq[8] = k + 2;
+          if (pend >= 0) pend = ws_claim(fp, total);
+        }
+        ws_bar_r();
+        item = sq[k & (WS_QN - 1)];
+        if (item < 0) break;
+      } else {
+        item = (int)blockIdx.x + k * stride;
+        if (item >= total) break;
+      }
       const int b = item / fp.segs;
       const ClipInfo c = clip_info(p, b);
       const WsItem it = ws_item<STATS>(p, fp, c, item);
@@ -494,7 +537,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     float* Ebuf = ebuf + wf * FK_EBUF;
     int gch = 0;                                                 // chunks / pass slots of the items this CTA has finished
     unsigned gpp = 0;
-    for (int item = blockIdx.x; item < total; item += stride) {
+    for (int k = 0;; ++k) {
+      int item;
+      if (dyn) {
+        if (lane == 0) {
+          sq[16 + wf] = k;                                       // items before step k are finished
+          while (sq[8] <= k) { }
+        }
+        __syncwarp();
+        item = sq[k & (WS_QN - 1)];
+        if (item < 0) break;
+      } else {
+        item = (int)blockIdx.x + k * stride;
+        if (item >= total) break;
+      }
       const int b = item / fp.segs;
       const ClipInfo c = clip_info(p, b);
       const WsItem it = ws_item<STATS>(p, fp, c, item);

@@ -303,3 +303,44 @@ def test_persistent_launch_is_bit_identical_to_one_cta_per_item(b2, O, monkeypat
         sums.append(ds.sums.cpu().numpy())
     assert sums[0][-1] == sums[1][-1] == float(nfr_p.sum().item())
     np.testing.assert_allclose(sums[0], sums[1], rtol=1e-11, atol=1e-6)
+
+
+def test_dynamic_persistent_launch_on_ragged_batches(b2, O, monkeypatch):
+    """Ragged batches larger than one wave: one CTA per SM, items claimed from a global counter and handed from the
+    resampler warps to the frame warps through a shared-memory queue (B200FBANK_PERSIST=2, the default for ragged
+    input) == one CTA per item (=0), bit for bit, including empty and too-short clips in the middle of the batch."""
+    B = 700
+    table = (22050, 44100, 48000, 16000)
+    g = torch.Generator().manual_seed(404)
+    rid = torch.randint(0, 4, (B,), generator=g)
+    dur = 0.2 + 0.9 * torch.rand(B, generator=g)
+    lens = (dur * torch.tensor(table)[rid]).long()
+    lens[5] = 0                                           # an empty clip
+    lens[300:310] = 100                                   # shorter than one 25 ms window: zero frames, pad rows only
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    flat = (torch.rand(int(offsets[-1]), generator=g) * 2 - 1).cuda()
+    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    random.seed(9)
+    masks = b2.specaugment.draw_masks(B, 128, 128, 32, 16, variant="reference")
+    kw = dict(out_frames=128, offsets=offsets, rate_ids=rid.int(), masks=masks, mean=AST_MEAN, std=AST_STD)
+    outs = {}
+    for flag in ("2", "0", "2"):
+        monkeypatch.setenv("B200FBANK_PERSIST", flag)
+        out, nfr = fe(flat, **kw)
+        torch.cuda.synchronize()
+        if flag in outs:
+            assert torch.equal(out, outs[flag][0])            # the claim order varies from run to run, the result does not
+        outs[flag] = (out, nfr)
+    assert torch.equal(outs["2"][1], outs["0"][1]) and torch.equal(outs["2"][0], outs["0"][0])
+    nfr = outs["2"][1].cpu()
+    assert int(nfr[5]) == 0 and bool((nfr[300:310] == 0).all())
+    want = [min(128, fe.num_frames(int(n), int(r))) for n, r in zip(lens, rid)]
+    assert nfr.tolist() == want
+    monkeypatch.delenv("B200FBANK_PERSIST")
+    raw, _ = fe(flat, out_frames=128, offsets=offsets, rate_ids=rid.int())
+    for i in (0, 1, 299, 311, 699):
+        w = flat[int(offsets[i]):int(offsets[i + 1])].cpu().numpy()
+        ref = O.kaldi_fbank(O.resample(w, table[int(rid[i])], 16000), O.ast_fbank_options())
+        m = min(ref.shape[0], 128)
+        assert m == int(nfr[i])
+        assert_logmel_close(raw[i, :m].cpu().numpy(), ref[:m], LOGMEL_TOL, f"ragged clip {i}")
