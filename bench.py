@@ -417,6 +417,20 @@ def run_extra(args, rank, local_rank, world):
                                   value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
                                   roofline_frac=B * (CLIP_SAMPLES * 4 + OUT_FRAMES * N_MELS * 4) / (ms * 1e-3) / 1e9 / measured_peaks()[0]))
             del wav, out
+    elif args.workload == "mixup":
+        # 1024 AST spectrograms (1, 128, 512) mixed with partners from a 2048-clip bank; every
+        # sample mixed (2 reads + 1 write per element), so the algorithmic bytes are 3 x 268 MB
+        B, NB = 1024, 2048
+        x = torch.randn((B, 1, N_MELS, OUT_FRAMES), generator=gen, device=dev)
+        bank = torch.randn((NB, 1, N_MELS, OUT_FRAMES), generator=gen, device=dev)
+        g = torch.Generator().manual_seed(5 + rank)
+        plan = b2.MixupPlan(torch.randint(0, NB, (B,), generator=g).int(), torch.rand(B, generator=g)).to(dev)
+        out = torch.empty_like(x)
+        ms = timed(lambda: b2.mixup_batch(x, bank, plan, out=out), args.steps)
+        alg = 3 * B * N_MELS * OUT_FRAMES * 4
+        out_lines.append(dict(workload="mixup: 1024 x (1,128,512) spectrograms, partners from a 2048-clip bank, all mixed",
+                              ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                              roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], algorithmic_bytes_per_launch=alg))
     if rank == 0:
         for d in out_lines:
             print(json.dumps(dict(metric=METRIC, n_gpus=world, dtype="f32", data="synthetic", **d)), flush=True)
@@ -432,7 +446,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep"],
+    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup"],
                     help="esc50 = the headline line (BASELINE.json configs[1]); the others are documentation runs")
     ap.add_argument("--clips", type=int, default=100000, help="clips of the stats workload")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per pipelined chunk of the host-in/host-out path")

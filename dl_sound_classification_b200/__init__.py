@@ -10,10 +10,12 @@ from .frontend import AST_FBANK_KWARGS, FbankFrontend, MelSpecFrontend, launch_c
 from .kaldi import fbank
 from .preprocessing import (ASTPreprocessor, B200ASTPreprocessor, BasePreprocessor, PreprocessingConfig,
                             create_preprocessor, melspectrogram, resample_waveform)
+from .mixup import MixupAugmentation, MixupPlan, draw_mixup_plan, mixup_batch, mixup_labels
 from .specaugment import SpecAugment
 from .stats import DatasetStats, NormStats, finalize_sums
 
 __all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi", "ASTPreprocessor",
            "B200ASTPreprocessor", "BasePreprocessor", "PreprocessingConfig", "create_preprocessor",
-           "resample_waveform", "melspectrogram", "MelSpecFrontend", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums"]
+           "resample_waveform", "melspectrogram", "MelSpecFrontend", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums",
+           "MixupAugmentation", "MixupPlan", "draw_mixup_plan", "mixup_batch", "mixup_labels"]
 __version__ = "0.1.0"

@@ -22,6 +22,7 @@
 #include "fbank_generic.cuh"
 #include "fbank_fast.cuh"
 #include "fbank_ws.cuh"
+#include "mixup.cuh"
 #include <cstdlib>
 
 namespace {
@@ -1018,6 +1019,34 @@ extern "C" int b200fbank_debug_ws_timing(unsigned long long out[8]) {
   return 0;
 }
 #endif
+
+int b200fbank_mixup(const float* d_x, const float* d_bank, const int32_t* d_partner, const float* d_lam, int B,
+                    int64_t clip_elems, float* d_out, void* stream) {
+  if (B < 0 || clip_elems <= 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0 and clip_elems > 0");
+  if (B == 0) return 0;
+  if (!d_x || !d_bank || !d_partner || !d_lam || !d_out) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
+  if (B > 65535) return fail(B200FBANK_ERR_INVALID, "B = %d exceeds the grid limit 65535 of the mixup launch", B);
+  const int64_t per_cta = (int64_t)b200::MIX_THREADS * b200::MIX_VEC_PER_THREAD * 4;
+  const int64_t tiles = (clip_elems + per_cta - 1) / per_cta;
+  if (tiles > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "clip_elems too large");
+  b200::mixup_kernel<<<dim3((unsigned)tiles, (unsigned)B), b200::MIX_THREADS, 0, (cudaStream_t)stream>>>(
+      d_x, d_bank, d_partner, d_lam, clip_elems, d_out);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200fbank_mixup_labels(const int64_t* d_label, const int64_t* d_partner_label, const int32_t* d_partner,
+                           const float* d_lam, int B, int num_classes, float* d_soft, void* stream) {
+  if (B < 0 || num_classes <= 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0 and num_classes > 0");
+  if (B == 0) return 0;
+  if (!d_label || !d_partner_label || !d_partner || !d_lam || !d_soft) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
+  b200::mixup_labels_kernel<<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(d_label, d_partner_label, d_partner, d_lam, B,
+                                                                          num_classes, d_soft);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 int64_t b200fbank_launch_count(int reset) {
   int64_t n = g_launches;

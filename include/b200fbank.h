@@ -197,6 +197,22 @@ int b200fbank_resample(const b200fbank_plan* p, const float* d_wav, const int64_
                        int64_t clip_samples, const int32_t* d_rate_id, int B, float* d_out,
                        const int64_t* d_out_offsets, int64_t out_clip_samples, void* stream);
 
+/* Mixup of a batch with partners from a feature bank, the arithmetic of
+   MixupAugmentation.__call__ (src/datasets/preprocessing.py:933-968) applied to sample i of d_x with
+   d_bank[d_partner[i]] as the reference's MixupDataset.apply_mixup pairs them (src/datasets/esc50.py:43-76):
+     out[i] = lam[i] * x[i] + (1 - lam[i]) * bank[partner[i]]     (float32, the reference's order of roundings)
+   d_partner[i] < 0: sample i is not mixed, out[i] = x[i].  Rows are clip_elems floats; d_out may alias d_x.
+   The random draws (who is mixed, with whom, lambda ~ Beta) are host logic: dl_sound_classification_b200/mixup.py
+   replays the reference's generators in the reference's order.  No plan is needed. */
+int b200fbank_mixup(const float* d_x, const float* d_bank, const int32_t* d_partner, const float* d_lam, int B,
+                    int64_t clip_elems, float* d_out, void* stream);
+
+/* Soft labels of the same mix: d_soft[B][num_classes] = 0, then [label] = lam and [partner_label] = 1 - lam, in
+   this order (equal labels leave 1 - lam, preprocessing.py:962-966); one-hot for unmixed samples
+   (create_one_hot_labels, preprocessing.py:39-52). */
+int b200fbank_mixup_labels(const int64_t* d_label, const int64_t* d_partner_label, const int32_t* d_partner,
+                           const float* d_lam, int B, int num_classes, float* d_soft, void* stream);
+
 /* Number of kernel launches the calls above issued on this thread since the last reset
    (bench.py's gpu_launches claim). */
 int64_t b200fbank_launch_count(int reset);
