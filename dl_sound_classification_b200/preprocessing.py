@@ -9,8 +9,9 @@ configs untouched): ``frontend`` ("kaldi_fbank", the north_
 ``target_sample_rate`` (16000), ``target_frames`` (None = the clip's own frame count),
 ``window_type`` ("hanning"), ``norm_mean`` / ``norm_std`` (dataset statistics, scalar or
 per-bin; None + ``normalize`` = the reference's per-clip mean / unbiased std), ``extra_rates``.
-Out of scope: the gzip/pickle disk cache -- GPU recompute
-makes it moot, ``preprocess_with_cache`` simply recomputes -- and the EnvNet/CNN modes.
+The gzip/pickle disk cache is not consulted -- GPU recompute makes it moot, ``preprocess_with_cache``
+simply recomputes -- but ``cache.precompute_cache`` can WRITE it in the reference's format (row N4);
+the EnvNet/CNN modes are out of scope.
 """
 from __future__ import annotations
 
@@ -49,15 +50,21 @@ class PreprocessingConfig:
             system_info = {"python_version": platform.python_version(), "torch_version": torch.__version__,
                            "platform": platform.platform()}
 
-            def plain(obj):
-                if hasattr(obj, "_content") and hasattr(obj, "items"):
-                    return {k: plain(v) for k, v in obj.items()}
-                if isinstance(obj, (list, tuple)):
-                    return [plain(v) for v in obj]
-                if isinstance(obj, torch.Tensor):
-                    return obj.tolist()
-                return obj
-            s = json.dumps({"config": plain(self.config), "system_info": system_info}, sort_keys=True, default=str)
+            # the reference's own conversion, quirk included (src/datasets/preprocessing.py:631-641): an omegaconf
+            # DictConfig becomes a dict, but anything else that is iterable and indexable -- a plain dict too --
+            # becomes the list of its items, i.e. a plain dict hashes by its KEYS only.  Reproduced literally so that
+            # cache directories and cache file names agree with an unmodified reference checkout.
+            def convert_omegaconf(obj):
+                if hasattr(obj, "_content"):
+                    return {k: convert_omegaconf(v) for k, v in obj.items()}
+                elif hasattr(obj, "__iter__") and hasattr(obj, "__getitem__") and not isinstance(obj, str):
+                    try:
+                        return [convert_omegaconf(item) for item in obj]
+                    except Exception:
+                        return obj
+                else:
+                    return obj
+            s = json.dumps({"config": convert_omegaconf(self.config), "system_info": system_info}, sort_keys=True)
             self._hash = hashlib.md5(s.encode()).hexdigest()[:12]
         return self._hash
 
@@ -102,8 +109,11 @@ class BasePreprocessor(ABC):
         return [self.preprocess(waveform, self.config.config.get("sample_rate", 44100))]
 
     def setup_cache(self, base_cache_dir: Path, force_rebuild: bool = False, max_cache_size_gb: float = 5.0) -> None:
-        """Accepted for signature compatibility; features are recomputed on the GPU, never cached."""
+        """src/datasets/preprocessing.py:716-731.  Only the cache DIRECTORY is remembered: per-clip calls recompute on
+        the GPU (faster than gunzip + unpickle), while ``cache.precompute_cache`` can fill that directory in the
+        reference's own file format for consumers that still read it."""
         self.cache_manager = None
+        self.cache_dir = Path(base_cache_dir) / self.get_cache_suffix()
 
     def preprocess_with_cache(self, waveform: torch.Tensor, sample_rate: int,
                               original_path: Optional[Path] = None) -> torch.Tensor:
@@ -177,7 +187,13 @@ class ASTPreprocessor(BasePreprocessor):
         self._device = device
         self._kw = kw
         self._fe: Optional[FbankFrontend] = None
-        self.mixup = None
+        # Mixup augmentation (src/datasets/preprocessing.py:999-1008)
+        mixup_config = c.get("mixup", {}) or {}
+        if mixup_config.get("enabled", False):
+            from .mixup import MixupAugmentation
+            self.mixup = MixupAugmentation(alpha=mixup_config.get("alpha", 0.5), prob=mixup_config.get("prob", 0.5))
+        else:
+            self.mixup = None
 
     # the plan is created lazily so that constructing the object needs no GPU (config plumbing, hashing)
     @property
@@ -287,8 +303,14 @@ class ASTPreprocessor(BasePreprocessor):
         """Mask table for the fused path; same RNG consumption as ``batch`` sequential ``apply_specaugment`` calls."""
         return _sa.draw_masks(batch, n_frames, int(self.n_mels), time_mask, freq_mask, "reference", random)
 
-    def apply_mixup(self, spec1, spec2, label1, label2, num_classes):
-        raise NotImplementedError("mixup is the step after the frontend (SURVEY.md section 8f N3), not built yet")
+    def apply_mixup(self, spec1: torch.Tensor, spec2: torch.Tensor, label1: int, label2: int, num_classes: int):
+        """src/datasets/preprocessing.py:1106-1113: mix if enabled in the config, else the original with one-hot
+        labels.  Batches should use ``mixup.draw_mixup_plan`` + ``mixup.mixup_batch`` (one launch) instead."""
+        if self.mixup:
+            return self.mixup(spec1, spec2, label1, label2, num_classes)
+        labels = torch.zeros(num_classes, dtype=torch.float32)
+        labels[label1] = 1.0
+        return spec1, labels
 
 
 B200ASTPreprocessor = ASTPreprocessor
