@@ -85,6 +85,8 @@ def _load():
     lib.b200fbank_mixup.restype = C.c_int
     lib.b200fbank_mixup_labels.argtypes = [VP, VP, VP, VP, C.c_int, C.c_int, VP, VP]
     lib.b200fbank_mixup_labels.restype = C.c_int
+    lib.b200fbank_patch_embed.argtypes = [VP, C.c_int, C.c_int, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, VP, C.c_int, VP]
+    lib.b200fbank_patch_embed.restype = C.c_int
     lib.b200fbank_launch_count.argtypes = [C.c_int]
     lib.b200fbank_launch_count.restype = I64
     lib.b200fbank_sizeof_opts.restype = C.c_int
@@ -100,7 +102,7 @@ lib = _load()
 
 EXPORTED_SYMBOLS = [
     "b200fbank_abi_version", "b200fbank_sizeof_opts", "b200fbank_default_opts", "b200fbank_plan_create", "b200fbank_plan_destroy",
-    "b200fbank_last_error", "b200fbank_mixup", "b200fbank_mixup_labels", "b200fbank_resampled_length", "b200fbank_num_frames", "b200fbank_num_cols",
+    "b200fbank_last_error", "b200fbank_mixup", "b200fbank_mixup_labels", "b200fbank_patch_embed", "b200fbank_resampled_length", "b200fbank_num_frames", "b200fbank_num_cols",
     "b200fbank_plan_table", "b200fbank_plan_info", "b200fbank_execute", "b200fbank_melspec_db",
     "b200fbank_stats_accumulate",
     "b200fbank_resample", "b200fbank_launch_count",

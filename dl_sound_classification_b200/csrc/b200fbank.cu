@@ -23,6 +23,7 @@
 #include "fbank_fast.cuh"
 #include "fbank_ws.cuh"
 #include "mixup.cuh"
+#include "patch_embed.cuh"
 #include <cstdlib>
 
 namespace {
@@ -1043,6 +1044,38 @@ int b200fbank_mixup_labels(const int64_t* d_label, const int64_t* d_partner_labe
   if (!d_label || !d_partner_label || !d_partner || !d_lam || !d_soft) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
   b200::mixup_labels_kernel<<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(d_label, d_partner_label, d_partner, d_lam, B,
                                                                           num_classes, d_soft);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200fbank_patch_embed(const float* d_feat, int B, int F, int T, const void* d_weight_f16, const float* d_bias, int D,
+                          int patch, int stride, void* d_out, int out_f16, void* stream) {
+  if (B < 0 || F <= 0 || T <= 0 || D <= 0 || stride <= 0) return fail(B200FBANK_ERR_INVALID, "bad shape");
+  if (patch != 16) return fail(B200FBANK_ERR_UNSUPPORTED, "patch size %d: only the 16 x 16 patches of AST are built", patch);
+  if (D % b200::PE_N) return fail(B200FBANK_ERR_UNSUPPORTED, "embedding dim %d is not a multiple of %d", D, b200::PE_N);
+  if (F < patch || T < patch) return fail(B200FBANK_ERR_INVALID, "spectrogram %d x %d is smaller than one patch", F, T);
+  if (B == 0) return 0;
+  if (!d_feat || !d_weight_f16 || !d_out) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
+  b200::PatchEmbedParams k;
+  k.feat = d_feat; k.w = (const __half*)d_weight_f16; k.bias = d_bias; k.out = d_out;
+  k.B = B; k.F = F; k.T = T; k.D = D; k.stride = stride; k.out_f16 = out_f16;
+  k.Fp = (F - patch) / stride + 1; k.Tp = (T - patch) / stride + 1;
+  k.M = (int64_t)B * k.Fp * k.Tp;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int NT = D / b200::PE_N;
+  const int64_t m_tiles = (k.M + b200::PE_M - 1) / b200::PE_M;
+  int per_col = (int)std::min<int64_t>(m_tiles, std::max(1, sms / NT));
+  const unsigned grid = (unsigned)(per_col * NT);
+  if (out_f16) {
+    CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PE_SMEM));
+    b200::patch_embed_kernel<true><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PE_SMEM));
+    b200::patch_embed_kernel<false><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;

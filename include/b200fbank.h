@@ -213,6 +213,15 @@ int b200fbank_mixup(const float* d_x, const float* d_bank, const int32_t* d_part
 int b200fbank_mixup_labels(const int64_t* d_label, const int64_t* d_partner_label, const int32_t* d_partner,
                            const float* d_lam, int B, int num_classes, float* d_soft, void* stream);
 
+/* AST patch embedding fed from the frontend's features: Conv2d(1, D, patch, stride) on
+   d_feat (B, 1, F, T) float32 -> d_out (B, Fp * Tp, D), patch index Fp-major as flatten(2).transpose(1, 2) leaves it
+   (PatchEmbed.forward, src/models/ast_mini.py:7-15; ASTModel.forward, src/models/ast.py:30,50-56).  An im2col GEMM on
+   the 5th-generation tensor cores (tcgen05.mma, fp16 operands as under the reference's "16-mixed" AST setting, fp32
+   accumulation in TMEM).  d_weight_f16: (D, patch * patch) fp16 = weight[d][0][i][j] at patch * i + j; d_bias (D) float32 or
+   NULL; d_out fp16 (out_f16 != 0) or float32.  Built for patch == 16 and D a multiple of 192 (192 / 384 / 768). */
+int b200fbank_patch_embed(const float* d_feat, int B, int F, int T, const void* d_weight_f16, const float* d_bias, int D,
+                          int patch, int stride, void* d_out, int out_f16, void* stream);
+
 /* Number of kernel launches the calls above issued on this thread since the last reset
    (bench.py's gpu_launches claim). */
 int64_t b200fbank_launch_count(int reset);
