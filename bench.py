@@ -431,9 +431,25 @@ def run_extra(args, rank, local_rank, world):
         out_lines.append(dict(workload="mixup: 1024 x (1,128,512) spectrograms, partners from a 2048-clip bank, all mixed",
                               ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
                               roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], algorithmic_bytes_per_launch=alg))
+    elif args.workload == "patch_embed":
+        # SURVEY.md section 8f N2 / BASELINE.json configs[4] tail: 1024 AST spectrograms (1, 128, 512) -> Conv2d(1, 768, 16,
+        # stride 10) as a tcgen05 im2col GEMM -> (1024, 600, 768) fp16.  Algorithmic bytes: features in + embeddings out.
+        B, D = 1024, 768
+        x = torch.randn((B, 1, N_MELS, OUT_FRAMES), generator=gen, device=dev) * 0.5
+        torch.manual_seed(7)
+        conv = torch.nn.Conv2d(1, D, 16, stride=10).to(dev)
+        w16, bias = conv.weight.detach(), conv.bias.detach()
+        ms = timed(lambda: b2.patch_embed(x, w16, bias, 10, torch.float16), args.steps)
+        npatch = 12 * ((OUT_FRAMES - 16) // 10 + 1)
+        alg = B * N_MELS * OUT_FRAMES * 4 + B * npatch * D * 2 + D * 256 * 2
+        flops = 2.0 * B * npatch * 256 * D
+        out_lines.append(dict(workload="patch_embed: 1024 x (1,128,512) -> Conv2d(1,768,16,stride 10) -> (1024,600,768) fp16 (tcgen05)",
+                              ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                              roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], algorithmic_bytes_per_launch=alg,
+                              tflops=flops / (ms * 1e-3) / 1e12, dtype="f16"))
     if rank == 0:
         for d in out_lines:
-            print(json.dumps(dict(metric=METRIC, n_gpus=world, dtype="f32", data="synthetic", **d)), flush=True)
+            print(json.dumps(dict(dict(metric=METRIC, n_gpus=world, dtype="f32", data="synthetic"), **d)), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -446,7 +462,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup"],
+    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup", "patch_embed"],
                     help="esc50 = the headline line (BASELINE.json configs[1]); the others are documentation runs")
     ap.add_argument("--clips", type=int, default=100000, help="clips of the stats workload")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per pipelined chunk of the host-in/host-out path")

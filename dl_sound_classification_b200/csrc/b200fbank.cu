@@ -1081,6 +1081,15 @@ int b200fbank_patch_embed(const float* d_feat, int B, int F, int T, const void* 
   return 0;
 }
 
+#ifdef B200_PE_TIMING
+extern "C" int b200fbank_debug_pe_timing(unsigned long long out[4]) {
+  unsigned long long z[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out, b200::g_pe_timing, sizeof z) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(b200::g_pe_timing, z, sizeof z);
+  return 0;
+}
+#endif
+
 int64_t b200fbank_launch_count(int reset) {
   int64_t n = g_launches;
   if (reset) g_launches = 0;

@@ -23,7 +23,7 @@ constexpr int PE_NKB = PE_K / PE_KB;                   // 4
 constexpr int PE_A_KB_BYTES = PE_M * 128;              // 16 KB per k-block of A
 constexpr int PE_B_KB_BYTES = PE_N * 128;              // 24 KB per k-block of W
 constexpr int PE_TMEM_COLS = 256;                      // power of two >= PE_N
-constexpr size_t PE_SMEM = 1024 + (size_t)PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + 64;
+constexpr size_t PE_SMEM = 1024 + (size_t)PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + 64 + PE_N * 4 + 8 * 32 * 208;
 
 struct PatchEmbedParams {
   const float* feat;       // (B, 1, F, T)
@@ -61,6 +61,13 @@ __device__ __forceinline__ void pe_mbar_wait(uint32_t bar, unsigned parity) {
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+#ifdef B200_PE_TIMING
+__device__ unsigned long long g_pe_timing[4];
+#define PE_T(slot, since) do { if (tid == 0) atomicAdd(&g_pe_timing[slot], (unsigned long long)(clock64() - (since))); } while (0)
+#else
+#define PE_T(slot, since)
+#endif
+
 template <bool OUT_F16>
 __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchEmbedParams p) {
   extern __shared__ uint8_t pe_smem_raw[];
@@ -72,6 +79,8 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
   const uint32_t sB_a = base, sA_a = base + PE_NKB * PE_B_KB_BYTES;
   const uint32_t bar_a = sA_a + PE_NKB * PE_A_KB_BYTES;                 // mbarrier (8 B) + TMEM base address (4 B)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + 16);
+  float* sbias = reinterpret_cast<float*>(gen + PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + 64);   // [192] bias of the CTA's columns
+  uint8_t* sStage = gen + PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + 64 + PE_N * 4;               // [8 warps][32 rows][208 B]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NT = p.D / PE_N;
@@ -94,6 +103,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(n0 + n) * PE_K) + ch);
     *reinterpret_cast<uint4*>(sB + (ch >> 3) * PE_B_KB_BYTES + pe_swz(n, ch & 7)) = v;
   }
+  for (int i = tid; i < PE_N; i += PE_THREADS) sbias[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -106,6 +116,9 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
   unsigned phase = 0;
   for (int64_t mt = cta_in_col; mt < m_tiles; mt += ctas_per_col) {
     // ---- A tile: 128 patches x 256 taps, fp32 -> fp16, swizzled ------------------------------------------------
+#ifdef B200_PE_TIMING
+    const long long t0_ = clock64();
+#endif
     {
       const int64_t m = mt * PE_M + row;
       const bool live = m < p.M;
@@ -114,30 +127,37 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
       const int pp = live ? (int)(m - (int64_t)b * per) : 0;
       const int hp = pp / p.Tp, wp = pp - hp * p.Tp;
       const float* src = p.feat + ((size_t)b * p.F + (size_t)hp * p.stride) * p.T + (size_t)wp * p.stride;
-#pragma unroll 4
+      // all 16 x 4 loads of the thread are issued before the first conversion: the gather is latency-bound
+      const bool al8 = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(p.T * 4)) & 7) == 0;
+      float2 f[16][4];
+#pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int ch = cbase + 2 * u;                                   // chunk of 8 taps: i = ch >> 1, j = 8 (ch & 1) ..
         const float* s = src + (size_t)(ch >> 1) * p.T + 8 * (ch & 1);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (live) {
-          float f[8];
-          if ((reinterpret_cast<uintptr_t>(s) & 7) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(s) + q); f[2 * q] = t2.x; f[2 * q + 1] = t2.y; }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = __ldg(s + q);
-          }
-          __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-          __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
-          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+        for (int q = 0; q < 4; ++q) {
+          if (!live) f[u][q] = make_float2(0.f, 0.f);
+          else if (al8) f[u][q] = __ldg(reinterpret_cast<const float2*>(s) + q);
+          else f[u][q] = make_float2(__ldg(s + 2 * q), __ldg(s + 2 * q + 1));
         }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int ch = cbase + 2 * u;
+        __half2 h0 = __floats2half2_rn(f[u][0].x, f[u][0].y), h1 = __floats2half2_rn(f[u][1].x, f[u][1].y);
+        __half2 h2 = __floats2half2_rn(f[u][2].x, f[u][2].y), h3 = __floats2half2_rn(f[u][3].x, f[u][3].y);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+        v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(sA + (ch >> 3) * PE_A_KB_BYTES + pe_swz(row, ch & 7)) = v;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the tensor core
     __syncthreads();
+#ifdef B200_PE_TIMING
+    PE_T(0, t0_);
+    const long long t1_ = clock64();
+#endif
     // ---- 16 MMAs (4 k-blocks x 4 x K16), one thread ------------------------------------------------------------
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -160,26 +180,47 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
     pe_mbar_wait(bar_a, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef B200_PE_TIMING
+    PE_T(1, t1_);
+    const long long t2_ = clock64();
+#endif
     // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .., columns 96 (w >> 2) ..; row = lane ---------------------
     {
       const int r = 32 * (warp & 3) + lane;
       const int64_t m = mt * PE_M + r;
       const int c0 = 96 * (warp >> 2);
-#pragma unroll 1
-      for (int cc = 0; cc < 6; ++cc) {
-        const int col = c0 + 16 * cc;
-        uint32_t v[16];
+      uint32_t v[6][16];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc)                                    // all six loads in flight, one wait
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < p.M) {
+                     : "=r"(v[cc][0]), "=r"(v[cc][1]), "=r"(v[cc][2]), "=r"(v[cc][3]), "=r"(v[cc][4]), "=r"(v[cc][5]), "=r"(v[cc][6]),
+                       "=r"(v[cc][7]), "=r"(v[cc][8]), "=r"(v[cc][9]), "=r"(v[cc][10]), "=r"(v[cc][11]), "=r"(v[cc][12]),
+                       "=r"(v[cc][13]), "=r"(v[cc][14]), "=r"(v[cc][15])
+                     : "r"(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(c0 + 16 * cc)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // bias, conversion, then a transpose through this warp's staging rows so that the global stores are whole
+      // contiguous row segments (a thread owns a ROW of the accumulator; row pitch of the output is D elements).
+      // Staging rows hold 192 B + 16 B pad (conflict-free 16-B writes): 96 fp16 columns at once, fp32 in two halves.
+      constexpr int EB = OUT_F16 ? 2 : 4;                               // bytes per output element
+      constexpr int HALVES = OUT_F16 ? 1 : 2, CCH = 6 / HALVES;         // 16-column groups per staging pass
+      constexpr int SROW = 208;
+      uint8_t* st = sStage + warp * (32 * SROW);
+      const int64_t m0 = mt * PE_M + 32 * (warp & 3);
+#pragma unroll
+      for (int hf = 0; hf < HALVES; ++hf) {
+#pragma unroll
+        for (int c2 = 0; c2 < CCH; ++c2) {
+          const int cc = hf * CCH + c2;
+          const int col = c0 + 16 * cc;
           float f[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]) + (p.bias ? __ldg(p.bias + n0 + col + q) : 0.f);
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(sbias + col + 4 * q);
+            f[4 * q] = __uint_as_float(v[cc][4 * q]) + bq.x; f[4 * q + 1] = __uint_as_float(v[cc][4 * q + 1]) + bq.y;
+            f[4 * q + 2] = __uint_as_float(v[cc][4 * q + 2]) + bq.z; f[4 * q + 3] = __uint_as_float(v[cc][4 * q + 3]) + bq.w;
+          }
+          uint8_t* d = st + lane * SROW + 16 * c2 * EB;
           if (OUT_F16) {
-            __half* o = reinterpret_cast<__half*>(p.out) + (size_t)m * p.D + n0 + col;
             uint4 a, b2;
             __half2 h;
             h = __floats2half2_rn(f[0], f[1]); a.x = *reinterpret_cast<uint32_t*>(&h);
@@ -190,18 +231,34 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_embed_kernel(const PatchE
             h = __floats2half2_rn(f[10], f[11]); b2.y = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(f[12], f[13]); b2.z = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(f[14], f[15]); b2.w = *reinterpret_cast<uint32_t*>(&h);
-            reinterpret_cast<uint4*>(o)[0] = a;
-            reinterpret_cast<uint4*>(o)[1] = b2;
+            reinterpret_cast<uint4*>(d)[0] = a;
+            reinterpret_cast<uint4*>(d)[1] = b2;
           } else {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.D + n0 + col;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(d)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
           }
         }
+        __syncwarp();
+        // 32 rows x 12 chunks of 16 B (192 B per row); consecutive lanes take consecutive chunks of a row
+#pragma unroll 4
+        for (int idx = lane; idx < 32 * 12; idx += 32) {
+          const int rr = idx / 12, ch = idx - rr * 12;
+          if (m0 + rr < p.M) {
+            const uint4 val = *reinterpret_cast<const uint4*>(st + rr * SROW + 16 * ch);
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + rr) * p.D + n0 + c0 + hf * (96 / HALVES)) * EB + 16 * ch;
+            __stcs(reinterpret_cast<uint4*>(o), val);
+          }
+        }
+        __syncwarp();
       }
+      (void)m; (void)r;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                                    // accumulator drained, A tile free again
+#ifdef B200_PE_TIMING
+    PE_T(2, t2_);
+    if (tid == 0) atomicAdd(&g_pe_timing[3], 1ull);
+#endif
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(PE_TMEM_COLS) : "memory");
 }
