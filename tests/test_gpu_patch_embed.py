@@ -36,7 +36,7 @@ def test_matches_the_reference_patch_embed_golden(b2):
     assert torch.equal(mod.cuda()(x[:, 0].cuda(), torch.float32).cpu(), got)
 
 
-@pytest.mark.parametrize("B,T,D", [(3, 512, 768), (5, 200, 384), (1, 16, 192), (130, 40, 192)])
+@pytest.mark.parametrize("B,T,D", [(3, 512, 768), (5, 200, 384), (1, 16, 192), (130, 40, 192), (2, 101, 192)])
 def test_against_torch_convolution(b2, B, T, D):
     torch.manual_seed(B * 1000 + T + D)
     x = (torch.randn(B, 1, 128, T) * 0.5).cuda()
