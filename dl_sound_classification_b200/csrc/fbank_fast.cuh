@@ -206,16 +206,6 @@ __device__ __forceinline__ void fk_fold_norm(const FbankParams& p, bool stats, b
   shift = (fmask || !norm) ? 0.f : fmaf(-__ldg(p.mean + si), s, p.target_mean);
 }
 
-// The same constants kept in shared memory ([row][32 lanes], one copy per CTA) and re-read at each use: frees 29
-// registers per thread for the FFT's instruction-level parallelism at the price of ~70 LDS per pass.
-struct FkLaneSm {
-  const float* base;    // rows: 0..12 window, 13..16 mstart (as int bits), 17..20 mbin (int bits), 21..24 scale, 25..28 shift; + lane
-  __device__ __forceinline__ float w(int j) const { return base[j * 32]; }
-  __device__ __forceinline__ int ms(int i) const { return __float_as_int(base[(13 + i) * 32]); }
-  __device__ __forceinline__ int bin(int i) const { return __float_as_int(base[(17 + i) * 32]); }
-  __device__ __forceinline__ float scale(int i) const { return base[(21 + i) * 32]; }
-  __device__ __forceinline__ float shift(int i) const { return base[(25 + i) * 32]; }
-};
 constexpr int FK_LANE_ROWS = 29;
 
 // DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.

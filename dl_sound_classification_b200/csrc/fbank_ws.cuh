@@ -1,21 +1,29 @@
-// Warp-specialised fused kernel for the AST configuration (same envelope as fbank_fast.cuh).
+// Warp-specialised, persistent fused kernel for the AST configuration (same envelope as fbank_fast.cuh).
 //
-// One CTA per SM, 384 threads = three warpgroups working as a producer/consumer pipeline over one
-// clip segment:
+// One CTA per SM, 384 threads = three warpgroups working as a producer/consumer pipeline:
 //
-//   warpgroup 0 (4 "R" warps, 232 registers/thread after setmaxnreg.inc): polyphase resampler.
-//     lane = phase group (5 phases); its 180 taps live in REGISTERS for the whole kernel, so the only
-//     shared-memory traffic of the stage is the input itself: 46 loads feed 90 packed FFMA2
-//     (fma.rn.f32x2) per 5 outputs.  In iteration i lane g works on hop (8*warp + i + skew[g]) mod 32;
-//     skew[g] = 9*(g - k0[g]) mod 32 makes the 32 lanes hit 32 distinct banks in every load (441 = 25 mod 32,
-//     25*9 = 1 mod 32), and the ring stride of 160 makes the 5-wide column stores conflict free too.
-//   warpgroups 1-2 (8 "F" warps, 136 registers/thread after setmaxnreg.dec): frame passes of
-//     fbank_fast.cuh (DC/pre-emphasis/window, packed 512-point FFT, |.|^2, mel, log, epilogue, store),
-//     pass p -> warp p mod 8.
+//   warpgroup 0 (4 "R" warps, 232 registers/thread after setmaxnreg.inc): polyphase resampler with the taps in
+//     REGISTERS, one mode per input rate (one chunk loop per mode, so only that mode's state is live):
+//       441 -> 160 (44.1 kHz): lane = phase group (5 phases, 180 taps); 46 loads feed 90 packed FFMA2 (fma.rn.f32x2) per
+//         5 outputs.  In iteration i lane g works on hop (8*warp + i + skew[g]) mod 32; skew[g] = 9*(g - k0[g]) mod 32
+//         makes the 32 lanes hit 32 distinct banks in every load (441 = 25 mod 32, 25*9 = 1 mod 32), and the ring
+//         stride of 160 makes the 5-wide column stores conflict free too.
+//       3 -> 1 (48 kHz): one phase of 41 taps shared by all lanes, held as even- and odd-aligned pairs.
+//       441 -> 320 (22.05 kHz): 320 phases = two hops; even / odd R warps hold the taps of even / odd hops.
+//       anything else: per-sample loop (16 kHz input: plain copy).
+//     Interior input chunks (32 hops) arrive by ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx), the next
+//     chunk is pulled into L2 by a bulk prefetch meanwhile; chunks at a clip edge are assembled with cp.async + zero fill.
+//   warpgroups 1-2 (8 "F" warps, 136 registers/thread after setmaxnreg.dec): frame passes of fbank_fast.cuh
+//     (DC/pre-emphasis/window, packed 512-point FFT, |.|^2, mel, log, epilogue, store), pass slot p -> warp p mod 8.
 //
-// The 16 kHz signal lives in a shared-memory ring of three 32-hop slots (+6 mirrored rows so every pass
-// reads 6 contiguous rows); slots are handed over with mbarriers (full: 128 R arrivals, empty: 256 F
-// arrivals).  R warps stream the input chunk by chunk with cp.async; nothing intermediate touches HBM.
+// The 16 kHz signal lives in a shared-memory ring of three 32-hop slots (+6 mirrored rows so every pass reads 6
+// contiguous rows); slots are handed over with mbarriers (full: 128 R arrivals, empty: 8 pass slots x 32 lanes).
+// Nothing intermediate touches HBM.
+//
+// Work distribution (fp.ws_persist): 0 = one item (clip segment) per CTA; 1 = grid of #SMs CTAs striding over the items
+// (dense batches); 2 = the same with items claimed from a global counter through a shared-memory queue (ragged
+// batches).  In the persistent forms ring slots, barrier phases and pass slots are numbered per CTA, so the pipeline
+// runs straight through clip boundaries.
 #pragma once
 #include "fbank_fast.cuh"
 
