@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
               lo = sq[16];
 #pragma unroll
               for (int w = 1; w < WS_F_WARPS; ++w) lo = min(lo, sq[16 + w]);
+              if (lo < k + 2 - WS_QN) __nanosleep(64);
             } while (lo < k + 2 - WS_QN);
           }
           sq[(k + 1) & (WS_QN - 1)] = pend;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       if (dyn) {
         if (lane == 0) {
           sq[16 + wf] = k;                                       // items before step k are finished
-          while (sq[8] <= k) { }
+          while (sq[8] <= k) __nanosleep(64);                    // published one item ahead: normally no wait at all
         }
         __syncwarp();
         item = sq[k & (WS_QN - 1)];
