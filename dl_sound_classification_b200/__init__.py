@@ -12,6 +12,7 @@ from .preprocessing import (ASTPreprocessor, B200ASTPreprocessor, BasePreprocess
                             create_preprocessor, melspectrogram, resample_waveform)
 from .cache import cache_path, file_hash, precompute_cache, read_cache_entry, write_cache_entry
 from .mixup import MixupAugmentation, MixupPlan, draw_mixup_plan, mixup_batch, mixup_labels
+from . import ops
 from .patch_embed import PatchEmbed, patch_embed
 from .specaugment import SpecAugment
 from .stats import DatasetStats, NormStats, finalize_sums
@@ -20,5 +21,5 @@ __all__ = ["FbankFrontend", "AST_FBANK_KWARGS", "fbank", "launch_count", "_capi"
            "B200ASTPreprocessor", "BasePreprocessor", "PreprocessingConfig", "create_preprocessor",
            "resample_waveform", "melspectrogram", "MelSpecFrontend", "SpecAugment", "DatasetStats", "NormStats", "finalize_sums",
            "precompute_cache", "read_cache_entry", "write_cache_entry", "cache_path", "file_hash",
-           "PatchEmbed", "patch_embed", "MixupAugmentation", "MixupPlan", "draw_mixup_plan", "mixup_batch", "mixup_labels"]
+           "ops", "PatchEmbed", "patch_embed", "MixupAugmentation", "MixupPlan", "draw_mixup_plan", "mixup_batch", "mixup_labels"]
 __version__ = "0.1.0"
