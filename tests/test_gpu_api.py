@@ -344,3 +344,23 @@ def test_dynamic_persistent_launch_on_ragged_batches(b2, O, monkeypatch):
         m = min(ref.shape[0], 128)
         assert m == int(nfr[i])
         assert_logmel_close(raw[i, :m].cpu().numpy(), ref[:m], LOGMEL_TOL, f"ragged clip {i}")
+
+
+def test_persistent_launch_with_a_non_ast_filterbank(b2, monkeypatch):
+    """The general (non-unrolled mel) instantiation of the warp-specialised kernel in its persistent form: 40 povey-windowed
+    bins at 16 kHz (kaldi defaults), no resampling: == one CTA per item, and == the single-clip kaldi.fbank drop-in."""
+    B, n = 400, 16000 + 123
+    g = torch.Generator().manual_seed(77)
+    wav = (torch.rand((B, n), generator=g) * 2 - 1).cuda()
+    fe = b2.FbankFrontend(orig_rates=(16000,), num_mel_bins=40, window_type="povey", sample_frequency=16000.0)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200FBANK_PERSIST", flag)
+        outs.append(fe(wav, out_frames=128))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    m = int(outs[0][1][0])
+    assert m == 99
+    for i in (0, 399):
+        one = b2.fbank(wav[i:i + 1], num_mel_bins=40)
+        assert torch.equal(outs[0][0][i, :m], one)
