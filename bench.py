@@ -431,6 +431,17 @@ def run_extra(args, rank, local_rank, world):
         out_lines.append(dict(workload="mixup: 1024 x (1,128,512) spectrograms, partners from a 2048-clip bank, all mixed",
                               ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
                               roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], algorithmic_bytes_per_launch=alg))
+    elif args.workload == "melspec":
+        # the reference's own ASTPreprocessor recipe (MelSpectrogram n_fft 1024 / hop 160 at 44.1 kHz,
+        # AmplitudeToDB top_db 80, per-clip mean / unbiased std normalisation) -> (B, 1, 128, 1379); generic kernel
+        B = 256
+        wav = torch.rand((B, CLIP_SAMPLES), generator=gen, device=dev) * 2 - 1
+        fe = b2.MelSpecFrontend(44100, 1024, 160, 400, N_MELS, 80.0, device=dev)
+        ms = timed(lambda: fe(wav, out_frames=1379), max(3, args.steps // 10))
+        alg = B * (CLIP_SAMPLES * 4 + N_MELS * 1379 * 4)
+        out_lines.append(dict(workload="melspec: reference-actual recipe, 256 ESC-50 clips -> (256,1,128,1379), dB + per-clip normalisation",
+                              ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                              roofline_frac=alg / (ms * 1e-3) / 1e9 / measured_peaks()[0], algorithmic_bytes_per_launch=alg))
     elif args.workload == "patch_embed":
         # SURVEY.md section 8f N2 / BASELINE.json configs[4] tail: 1024 AST spectrograms (1, 128, 512) -> Conv2d(1, 768, 16,
         # stride 10) as a tcgen05 im2col GEMM -> (1024, 600, 768) fp16.  Algorithmic bytes: features in + embeddings out.
@@ -462,7 +473,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup", "patch_embed"],
+    ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup", "patch_embed", "melspec"],
                     help="esc50 = the headline line (BASELINE.json configs[1]); the others are documentation runs")
     ap.add_argument("--clips", type=int, default=100000, help="clips of the stats workload")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per pipelined chunk of the host-in/host-out path")
