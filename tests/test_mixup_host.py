@@ -72,3 +72,13 @@ def test_mixup_has_no_cpu_path():
         b2.mixup_batch(x, bank, plan)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         b2.mixup_labels(labels, bank_labels, plan, C)
+
+
+def test_oracle_python_random_port_matches_cpython():
+    """The oracle's MT19937 port must replay CPython's random.random() / randint() stream bit for bit."""
+    for seed in (0, 1, 31337, 2 ** 40 + 7):
+        random.seed(seed)
+        rng = O.PyRandom(seed)
+        for _ in range(50):
+            assert O.py_random_float(rng) == random.random()
+            assert rng.randint(0, 1999) == random.randint(0, 1999)
