@@ -228,6 +228,7 @@ class FbankFrontend:
                 h_out[lo:hi].copy_(do, non_blocking=True)
         for st in state["streams"]:
             cur.wait_stream(st)
+            st.synchronize()        # "host buffers out": the D2H copies have LANDED when the caller gets h_out back
         return h_out
 
     def resample(self, wav: torch.Tensor, offsets: Optional[torch.Tensor] = None,

@@ -5,7 +5,8 @@ Same names, arguments and error behaviour as ``PreprocessingConfig`` (:612-680),
 (:61-76) and ``create_preprocessor`` (:1315-1346) -- computed by the fused sm_100a kernel.
 
 New OPTIONAL config keys (free-form kwargs already flow through the reference's Hydra
-configs untouched): ``frontend`` ("kaldi_fbank", the north_star recipe),
+configs untouched): ``frontend`` ("melspectrogram" = the reference's own recipe, the DEFAULT for a
+stock config; "kaldi_fbank" = the north_star recipe, also selected by giving ``target_sample_rate``),
 ``target_sample_rate`` (16000), ``target_frames`` (None = the clip's own frame count),
 ``window_type`` ("hanning"), ``norm_mean`` / ``norm_std`` (dataset statistics, scalar or
 per-bin; None + ``normalize`` = the reference's per-clip mean / unbiased std), ``extra_rates``.
@@ -169,7 +170,12 @@ class ASTPreprocessor(BasePreprocessor):
         self.target_mean = c.get("target_mean", 0.0)
         self.target_std = c.get("target_std", 0.5)
         self.normalize = c.get("normalize", True)
-        self.frontend_name = c.get("frontend", "kaldi_fbank")
+        # Default recipe = what the config's cache hash MEANS.  A stock reference config (no ``frontend`` /
+        # ``target_sample_rate`` key) hashes exactly as the reference hashes it, so it must produce the reference's own
+        # features: MelSpectrogram(1024/160 at sample_rate) + dB + per-clip normalisation, (1, 128, 1379) for 5 s.  The
+        # north_star kaldi recipe is opt-in (``frontend: kaldi_fbank`` or a ``target_sample_rate``); either key changes
+        # the hash, so its features can never land under the reference's stock cache key.
+        self.frontend_name = c.get("frontend", "kaldi_fbank" if "target_sample_rate" in c else "melspectrogram")
         self.target_sample_rate = int(c.get("target_sample_rate", 16000))
         self.target_frames = c.get("target_frames", None)
         self.window_type = c.get("window_type", "hanning")

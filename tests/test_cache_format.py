@@ -82,3 +82,16 @@ def test_round_trip_with_the_reference_cache_manager(tmp_path):
     assert torch.equal(CA.read_cache_entry(cdir, clip2, ours.get_hash()), x * 2)   # and we read theirs
     CA._update_metadata(cdir, [(clip, p)], ours.get_hash())
     assert str(clip) in R.AdvancedCacheManager(cdir).metadata["file_metadata"]     # their loader accepts our metadata file
+
+
+def test_stock_config_means_the_reference_recipe():
+    """A config the reference would hash identically must produce the reference's own features, so the default
+    frontend of a stock config (no ``frontend`` / ``target_sample_rate`` key) is the MelSpectrogram-dB recipe;
+    the kaldi recipe is opt-in and always changes the hash (its entries can never sit under the stock cache key)."""
+    stock = dict(sample_rate=44100, n_mels=128, bc_mixing=False, normalize=True, target_mean=0.0, target_std=0.5)
+    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(**stock))
+    assert pre.frontend_name == "melspectrogram"
+    k1 = b2.ASTPreprocessor(b2.PreprocessingConfig(**stock, frontend="kaldi_fbank"))
+    k2 = b2.ASTPreprocessor(b2.PreprocessingConfig(**stock, target_sample_rate=16000))
+    assert k1.frontend_name == k2.frontend_name == "kaldi_fbank"
+    assert len({pre.get_cache_suffix(), k1.get_cache_suffix(), k2.get_cache_suffix()}) == 3

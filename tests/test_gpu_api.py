@@ -31,7 +31,7 @@ def test_ast_preprocessor_per_clip_contract(b2, O):
     """preprocess(waveform[1,N] CPU, sr) -> [1, n_mels, T] on the input's device (preprocessing.py:1013)."""
     pre = b2.create_preprocessor("ast", dict(sample_rate=44100, n_mels=128, normalize=True, target_mean=0.0,
                                              target_std=0.5, norm_mean=AST_MEAN, norm_std=AST_STD,
-                                             target_frames=512), "/tmp/unused")
+                                             target_frames=512, frontend="kaldi_fbank"), "/tmp/unused")
     w = config1_clips(1)[0]
     out = pre.preprocess(w, 44100)
     assert out.device.type == "cpu" and tuple(out.shape) == (1, 128, 512) and out.dtype == torch.float32
@@ -41,10 +41,10 @@ def test_ast_preprocessor_per_clip_contract(b2, O):
     g = pre.preprocess(w.cuda(), 44100)
     assert g.is_cuda and torch.equal(g.cpu(), out)
     # natural frame count when target_frames is not configured
-    pre2 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False))
+    pre2 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False, target_sample_rate=16000))
     assert tuple(pre2.preprocess(w, 44100).shape) == (1, 128, 498)
     # per-clip normalisation (the reference's own convention: global mean / unbiased std, * 0.5)
-    pre3 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=True))
+    pre3 = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=True, frontend="kaldi_fbank"))
     x = pre3.preprocess(w, 44100)
     assert abs(float(x.mean())) < 1e-4 and abs(float(x.std()) - 0.5) < 1e-4
     with pytest.raises(AssertionError):
@@ -53,7 +53,7 @@ def test_ast_preprocessor_per_clip_contract(b2, O):
 
 def test_batch_with_fused_masks_matches_sequential_reference_calls(b2, O):
     pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, norm_mean=AST_MEAN, norm_std=AST_STD,
-                                                    target_frames=512))
+                                                    target_frames=512, frontend="kaldi_fbank"))
     clips = config1_clips(4, length=110250)
     random.seed(5)
     masks = pre.draw_specaugment_masks(4, 512, 192, 48)
@@ -68,7 +68,7 @@ def test_batch_with_fused_masks_matches_sequential_reference_calls(b2, O):
 
 
 def test_multi_crop_test(b2):
-    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False))
+    pre = b2.ASTPreprocessor(b2.PreprocessingConfig(sample_rate=44100, n_mels=128, normalize=False, frontend="kaldi_fbank"))
     w = short_clip(44100 * 7, seed=5)
     crops = pre.multi_crop_test(w)
     assert len(crops) == 10 and all(tuple(c.shape) == (1, 128, 498) for c in crops)
@@ -364,3 +364,17 @@ def test_persistent_launch_with_a_non_ast_filterbank(b2, monkeypatch):
     for i in (0, 399):
         one = b2.fbank(wav[i:i + 1], num_mel_bins=40)
         assert torch.equal(outs[0][0][i, :m], one)
+
+
+def test_process_host_matches_device_call(b2):
+    """Host buffers in / host buffers out (the e2e form bench.py times): the returned CPU tensor is complete when the
+    call returns (the side streams are synchronised) and equals the device-resident call bit for bit."""
+    fe = b2.FbankFrontend(orig_rates=(44100,), device="cuda:0", **b2.AST_FBANK_KWARGS)
+    clips = torch.cat(config1_clips(37, length=44100), 0)
+    h_wav = clips.pin_memory()
+    for layout in ("btf", "bft"):
+        want, _ = fe(clips.cuda(), out_frames=128, mean=AST_MEAN, std=AST_STD, layout=layout)
+        for chunk in (8, 64):
+            got = fe.process_host(h_wav, 128, chunk_clips=chunk, mean=AST_MEAN, std=AST_STD, layout=layout)
+            assert got.device.type == "cpu"
+            assert torch.equal(got, want.cpu()), (layout, chunk)

@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../dl_sound_classification_b200/csrc/taps_441_160.inc"
+#include "taps_441_160.inc"   // python tools/gen_taps_inc.py
 
 constexpr int RP = 5, LT = 36, WIN = 46, NG = 32;
 __constant__ float c_taps[NG * 180];
