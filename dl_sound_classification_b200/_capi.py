@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200fbank.so")
+LIB_PATH = os.environ.get("B200FBANK_LIB") or os.path.join(_HERE, "lib", "libb200fbank.so")   # env: kernel experiments (tools/ktime.py)
 ABI_VERSION = 1
 MAX_RATES = 8
 

@@ -513,29 +513,41 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   if (int rc = dev_copy(slot_start.data(), slot_start.size() * 4, (const void**)&f.mel_slot_start)) return rc;
   // ---- warp-specialised kernel: register-resident taps [32][5][36], even phase offsets ----------
   {
-    std::vector<float> wt((size_t)FK_NG * WS_GROUP_FLOATS, 0.f);
-    std::vector<int> wk(FK_NG, 0);
+    // two parity classes of tap windows (fbank_ws.cuh): class c of group g starts phase r at dense index
+    // wk[32 c + g] + ws_offc(c, r) and keeps WS_LT taps; the two starts of a group have opposite parity, so for every
+    // hop one of them sits on an even (8-byte aligned) sample address
+    std::vector<float> wt((size_t)2 * FK_NG * WS_GROUP_FLOATS, 0.f);
+    std::vector<int> wk(2 * FK_NG, 0);
     bool ok = f.fast_rate_id >= 0;
     if (ok) {
       const RateHost& r = p->rates[f.fast_rate_id];
       for (int g = 0; g < FK_NG && ok; ++g) {
-        int first[FK_RP], last[FK_RP], k0 = r.klen;
+        int first[FK_RP], last[FK_RP];
         for (int q = 0; q < FK_RP; ++q) {
           int a = r.klen, bb = -1;
           for (int k = 0; k < r.klen; ++k)
             if (std::fabs(r.dense[(size_t)(FK_RP * g + q) * r.klen + k]) > 1e-25f) { a = std::min(a, k); bb = std::max(bb, k); }
           first[q] = a; last[q] = bb;
-          k0 = std::min(k0, a - ws_off(q));
         }
-        k0 = std::max(k0, 0);
-        wk[g] = k0;
-        for (int q = 0; q < FK_RP; ++q) {
-          const int s0 = k0 + ws_off(q);
-          if (s0 > first[q] || last[q] >= s0 + WS_LT) ok = false;
-          for (int j = 0; j < WS_LT; ++j)
-            wt[(size_t)g * WS_GROUP_FLOATS + q * WS_LT + j] = (s0 + j < r.klen) ? r.dense[(size_t)(FK_RP * g + q) * r.klen + s0 + j] : 0.f;
+        for (int c = 0; c < 2 && ok; ++c) {
+          // every phase's non-zero taps must fall inside its window: k0 + off(r) in [last - (WS_LT - 1), first]
+          int lo = 0, hi = r.klen;
+          for (int q = 0; q < FK_RP; ++q) {
+            lo = std::max(lo, last[q] - (WS_LT - 1) - ws_offc(c, q));
+            hi = std::min(hi, first[q] - ws_offc(c, q));
+          }
+          hi = std::min(hi, r.klen + 8 - (ws_offc(c, FK_RP - 1) + WS_LT));      // stays inside the staged input tile
+          int k0 = hi;
+          if (c == 1 && ((k0 ^ wk[g]) & 1) == 0) --k0;                          // opposite parity to class 0
+          if (k0 < lo) { ok = false; break; }
+          wk[32 * c + g] = k0;
+          for (int q = 0; q < FK_RP; ++q) {
+            const int s0 = k0 + ws_offc(c, q);
+            for (int j = 0; j < WS_LT; ++j)
+              wt[((size_t)(32 * c + g) * FK_RP + q) * WS_LT + j] =
+                  (s0 + j >= 0 && s0 + j < r.klen) ? r.dense[(size_t)(FK_RP * g + q) * r.klen + s0 + j] : 0.f;
+          }
         }
-        if (k0 + ws_off(FK_RP - 1) + WS_LT > r.klen + 8) ok = false;      // stays inside the staged input tile
       }
     }
     const char* kenv = getenv("B200FBANK_KERNEL");

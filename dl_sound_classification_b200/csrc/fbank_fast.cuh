@@ -208,48 +208,55 @@ __device__ __forceinline__ void fk_fold_norm(const FbankParams& p, bool stats, b
 
 constexpr int FK_LANE_ROWS = 29;
 
+// Packed FP32 pairs: see fft_regs.cuh (fx_*).
+typedef fx2 fk_u64;
+__device__ __forceinline__ fk_u64 fk_pk(float lo, float hi) { return fx_pk(lo, hi); }
+__device__ __forceinline__ float2 fk_upk(fk_u64 v) { return fx_upk(v); }
+__device__ __forceinline__ fk_u64 fk_add2(fk_u64 a, fk_u64 b) { return fx_add(a, b); }
+__device__ __forceinline__ fk_u64 fk_sub2(fk_u64 a, fk_u64 b) { return fx_sub(a, b); }
+__device__ __forceinline__ fk_u64 fk_mul2(fk_u64 a, fk_u64 b) { return fx_mul(a, b); }
+__device__ __forceinline__ fk_u64 fk_fma2(fk_u64 a, fk_u64 b, fk_u64 c) { return fx_fma(a, b, c); }
+
 // DC removal + pre-emphasis + window for frames (row, row+1) -> packed complex z[n1], n = lane + 32 n1.
-// yb = ring + row * 161 + lane.  Loads are unconditional: every ring row holds finite data.   // [phase: stage0_frames]
+// yb = ring + row * RS + lane.  Loads are unconditional: every ring row holds finite data.   // [phase: stage0_frames]
+// The two frames of the pair are the two halves of f32x2 registers all the way (z[j] = (frame a, frame b) is exactly
+// such a pair): sum, DC subtraction and pre-emphasis are packed, in the reference's own order of roundings
+// (kaldi.py:183-204; the per-frame sum order and the fused multiply-add of the pre-emphasis are those of round 1).
 template <int RS, class LC>     // RS = ring hop stride in floats (160 = contiguous 16 kHz samples, 161 = padded rows)
 __device__ __forceinline__ void fk_stage0_pair(const float* __restrict__ yb, const LC& L, float dc_scale,
                                                float preemph, int lane, float2 (&z)[16]) {
   constexpr int PADR = RS - FK_SHIFT;      // extra floats per hop row
   const int d0 = lane == 0 ? 0 : 1;        // j = 0: replicate pad at the frame start (kaldi.py:195-198)
   const int d5 = lane == 0 ? 1 + PADR : 1; // j = 5, 10: n - 1 sits in the previous hop row
+  const float* ya = yb;                    // frame a
+  const float* yc = yb + RS;               // frame b = the next hop row
+  fk_u64 yv[13], s2 = 0ull;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float* y = yb + h * RS;
-    float yv[13], s = 0.f;
+  for (int j = 0; j < 13; ++j) {
+    const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+    yv[j] = fk_pk(ya[off], yc[off]);
+    if (j < 12) s2 = fk_add2(s2, yv[j]);
+  }
+  s2 = fk_add2(s2, lane < 16 ? yv[12] : 0ull);
 #pragma unroll
-    for (int j = 0; j < 13; ++j) {
-      yv[j] = y[32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0))];
-      if (j < 12) s += yv[j];
-    }
-    s += lane < 16 ? yv[12] : 0.f;
-    // (y[n] - mean) - c (y[n-1] - mean) = (y[n] - c y[n-1]) - (1 - c) mean: one fma, one add, one multiply per sample
-    const float mean1 = warp_sum(s) * dc_scale;          // dc_scale = (1 - c) / 400, or 0 without DC removal
-    const float* y0 = y - d0;
-    const float* y5 = y - d5;
+  for (int o = 16; o > 0; o >>= 1) s2 = fk_add2(s2, __shfl_xor_sync(0xffffffffu, s2, o));
+  const fk_u64 mean2 = fk_mul2(s2, fk_pk(dc_scale, dc_scale));     // dc_scale = 1 / 400, or 0 without DC removal
+  const fk_u64 npre2 = fk_pk(-preemph, -preemph);
 #pragma unroll
-    for (int j = 0; j < 13; ++j) {
-      const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
-      const float prev = (j == 0) ? y0[off] : ((j == 5 || j == 10) ? y5[off] : y[off - 1]);
-#ifdef B200_STAGE0_FOLD
-      const float v = (fmaf(-preemph, prev, yv[j]) - mean1) * L.w(j);
-#else
-      // the reference's own order of roundings (kaldi.py:183-204): errors stay correlated with torchaudio's
-      const float v = ((yv[j] - mean1) - preemph * (prev - mean1)) * L.w(j);
-#endif
-      if (h == 0) z[j].x = v; else z[j].y = v;
-    }
+  for (int j = 0; j < 13; ++j) {
+    const int off = 32 * j + PADR * (j >= 10 ? 2 : (j >= 5 ? 1 : 0));
+    const int po = (j == 0) ? off - d0 : ((j == 5 || j == 10) ? off - d5 : off - 1);
+    const fk_u64 prev = fk_pk(ya[po], yc[po]);
+    // (y[n] - mean) - c (y[n-1] - mean), then the window
+    const fk_u64 t = fk_fma2(npre2, fk_sub2(prev, mean2), fk_sub2(yv[j], mean2));
+    z[j] = fk_upk(fk_mul2(t, fk_pk(L.w(j), L.w(j))));            // SASS: FMUL2 with a broadcast .F32 operand
   }
 #pragma unroll
   for (int j = 13; j < 16; ++j) z[j] = make_float2(0.f, 0.f);
 }
 
-// 16-point DFT over n1, twiddle W_512^(lane k1), store row k1 of the exchange buffer.   // [phase: fft_stage1]
-__device__ __forceinline__ void fk_stage1_store(float2 (&z)[16], const float2* __restrict__ stw, int lane,
-                                                float2* __restrict__ E) {
+// 16-point DFT over n1 (in place, X[k1] ends up in z[bitrev(k1)]).   // [phase: fft_stage1]
+__device__ __forceinline__ void fk_dft16_pruned(float2 (&z)[16]) {
   // z[13..15] are the zero padding 400 -> 512: the first radix-2 stage has nothing to add or subtract there
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -260,12 +267,24 @@ __device__ __forceinline__ void fk_stage1_store(float2 (&z)[16], const float2* _
   }
   z[13] = mul_w32<10>(z[5]); z[14] = mul_w32<12>(z[6]); z[15] = mul_w32<14>(z[7]);
   DifStages<16, 4>::run(z);
-  E[lane] = z[0];
+}
+
+// a * w with the roundings of (fma(-a.y, w.y, a.x w.x), fma(a.y, w.x, a.x w.y)): FMUL2 + FFMA2
+__device__ __forceinline__ float2 fk_cmul(float2 a, float2 w) {
+  return fk_upk(fk_fma2(fk_pk(-w.y, w.x), fk_pk(a.y, a.y), fk_mul2(fk_pk(w.x, w.y), fk_pk(a.x, a.x))));
+}
+
+// Twiddle W_512^(lane k1) and store row k1 of the exchange buffers of BOTH packed transforms of the pass: the twiddle
+// is the same for the two, so it is read once.
+__device__ __forceinline__ void fk_stage1_store2(const float2 (&za)[16], const float2 (&zb)[16], const float2* __restrict__ stw,
+                                                 int lane, float2* __restrict__ EA, float2* __restrict__ EB) {
+  EA[lane] = za[0];
+  EB[lane] = zb[0];
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) {
     const float2 w = stw[k1 * 32 + lane];
-    const float2 a = z[bitrev_n(k1, 4)];
-    E[k1 * FK_EROW + lane] = make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+    EA[k1 * FK_EROW + lane] = fk_cmul(za[bitrev_n(k1, 4)], w);
+    EB[k1 * FK_EROW + lane] = fk_cmul(zb[bitrev_n(k1, 4)], w);
   }
 }
 
@@ -273,23 +292,26 @@ __device__ __forceinline__ void fk_stage1_store(float2 (&z)[16], const float2* _
 template <int MC>
 __device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, const float* __restrict__ wrow, int st,
                                              int mc_dyn, float (&acc)[4]) {
-  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  // frames (0,1) and (2,3) are the halves of two f32x2 accumulators: FFMA2 with the weight broadcast
+  fk_u64 a01 = 0ull, a23 = 0ull;
   if constexpr (MC >= 0) {
 #pragma unroll
     for (int j = 0; j < MC; ++j) {
       const float w = wrow[j * 32];
       const float4 pv = P4[st + j];
-      acc[0] = fmaf(w, pv.x, acc[0]); acc[1] = fmaf(w, pv.y, acc[1]);
-      acc[2] = fmaf(w, pv.z, acc[2]); acc[3] = fmaf(w, pv.w, acc[3]);
+      a01 = fk_fma2(fk_pk(w, w), fk_pk(pv.x, pv.y), a01);
+      a23 = fk_fma2(fk_pk(w, w), fk_pk(pv.z, pv.w), a23);
     }
   } else {
     for (int j = 0; j < mc_dyn; ++j) {
       const float w = wrow[j * 32];
       const float4 pv = P4[st + j];
-      acc[0] = fmaf(w, pv.x, acc[0]); acc[1] = fmaf(w, pv.y, acc[1]);
-      acc[2] = fmaf(w, pv.z, acc[2]); acc[3] = fmaf(w, pv.w, acc[3]);
+      a01 = fk_fma2(fk_pk(w, w), fk_pk(pv.x, pv.y), a01);
+      a23 = fk_fma2(fk_pk(w, w), fk_pk(pv.z, pv.w), a23);
     }
   }
+  const float2 r01 = fk_upk(a01), r23 = fk_upk(a23);
+  acc[0] = r01.x; acc[1] = r01.y; acc[2] = r23.x; acc[3] = r23.y;
 }
 
 // One frame pass of a warp: four consecutive frames starting at output row t0, whose samples start at
@@ -308,18 +330,16 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   const int nf = n_live;
   (void)mk2; (void)mk3;
   if (f0 < nf) {
-#ifdef B200_STAGE0_FOLD
-    const float dc_scale = p.remove_dc ? (1.f - p.preemph) / (float)FK_SIZE : 0.f;
-#else
     const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
-#endif
     // the two packed transforms (frames 0,1 and 2,3); unrolled so their dependency chains interleave (a rolled loop
     // halves the code but measured 3% slower: the pass is latency-bound, not instruction-cache bound)
-#pragma unroll
-    for (int tr = 0; tr < 2; ++tr) {
-      float2 z[16];
-      fk_stage0_pair<RS, LC>(rows + 2 * tr * RS + lane, L, dc_scale, p.preemph, lane, z);
-      fk_stage1_store(z, stw, lane, tr == 0 ? EA : EB);
+    {
+      float2 za[16], zb[16];
+      fk_stage0_pair<RS, LC>(rows + lane, L, dc_scale, p.preemph, lane, za);
+      fk_stage0_pair<RS, LC>(rows + 2 * RS + lane, L, dc_scale, p.preemph, lane, zb);
+      fk_dft16_pruned(za);
+      fk_dft16_pruned(zb);
+      fk_stage1_store2(za, zb, stw, lane, EA, EB);
     }
     __syncwarp();
     // ---- stage 2: lane = 2 k1 + transform gathers its row, 32-point DFT over n2   // [phase: exchange]
@@ -348,9 +368,10 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       // A = (Z[k] + conj Z[N-k]) / 2, B = (Z[k] - conj Z[N-k]) / 2i; the 1/4 (1/2 for magnitudes) is folded into
       // the mel weights on the host (exact: a power of two)
       const float2 sm = cadd(zk, make_float2(px, py)), df = csub(zk, make_float2(px, py));
-      float pa = fmaf(sm.x, sm.x, df.y * df.y), pb = fmaf(sm.y, sm.y, df.x * df.x);
-      if (!AST && !p.use_power) { pa = sqrtf(pa); pb = sqrtf(pb); }      // AST variant: power spectrum only
-      P2[32 * k2] = make_float2(pa, pb);
+      // (fma(sm.x, sm.x, df.y df.y), fma(sm.y, sm.y, df.x df.x)) as FMUL2 (swapped halves) + FFMA2
+      float2 pw = fk_upk(fk_fma2(fk_pk(sm.x, sm.y), fk_pk(sm.x, sm.y), fk_mul2(fk_pk(df.y, df.x), fk_pk(df.y, df.x))));
+      if (!AST && !p.use_power) { pw.x = sqrtf(pw.x); pw.y = sqrtf(pw.y); }      // AST variant: power spectrum only
+      P2[32 * k2] = pw;
     }
     __syncwarp();
   }
@@ -401,8 +422,9 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       } else {
         float* o = obase + moff;
         if (plain) {
-#pragma unroll
-          for (int h = 0; h < 4; ++h) o[h * ostep] = fmaf(v[h], L.scale(i), L.shift(i));
+          const fk_u64 sc2 = fk_pk(L.scale(i), L.scale(i)), sh2 = fk_pk(L.shift(i), L.shift(i));
+          const float2 y01 = fk_upk(fk_fma2(fk_pk(v[0], v[1]), sc2, sh2)), y23 = fk_upk(fk_fma2(fk_pk(v[2], v[3]), sc2, sh2));
+          o[0] = y01.x; o[ostep] = y01.y; o[2 * ostep] = y23.x; o[3 * ostep] = y23.y;
         } else {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {

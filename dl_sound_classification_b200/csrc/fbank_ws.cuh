@@ -4,10 +4,14 @@
 //
 //   warpgroup 0 (4 "R" warps, 232 registers/thread after setmaxnreg.inc): polyphase resampler with the taps in
 //     REGISTERS, one mode per input rate (one chunk loop per mode, so only that mode's state is live):
-//       441 -> 160 (44.1 kHz): lane = phase group (5 phases, 180 taps); 46 loads feed 90 packed FFMA2 (fma.rn.f32x2) per
-//         5 outputs.  In iteration i lane g works on hop (8*warp + i + skew[g]) mod 32; skew[g] = 9*(g - k0[g]) mod 32
-//         makes the 32 lanes hit 32 distinct banks in every load (441 = 25 mod 32, 25*9 = 1 mod 32), and the ring
-//         stride of 160 makes the 5-wide column stores conflict free too.
+//       441 -> 160 (44.1 kHz): lane = phase group (5 phases, 180 taps); 23 LDS.64 feed 90 packed FFMA2 (fma.rn.f32x2) per
+//         5 outputs.  A 64-bit load needs an even sample address and 441 is odd, so the R warps come in two classes
+//         whose tap windows start at dense indices of opposite parity (R warps 0-1: ws_k0g[g] + {0,2,4,6,10}; R warps
+//         2-3: ws_k0g[32 + g] + {0,2,4,8,10}): for every hop exactly one class reads lane g's window from an even
+//         address.  Inside a class lane g visits its 16 hops in the order m = (slot + skew[g]) mod 16, q = 2m + parity;
+//         skew[g] = 9*((g mod 16) - base[g]) mod 16 puts the 16 lanes of each half-warp on 16 distinct 8-byte bank
+//         pairs in every load (441 = 9 mod 16, 9*9 = 1 mod 16), and the ring stride of 160 keeps the 5-wide column
+//         stores conflict free whatever the hop.
 //       3 -> 1 (48 kHz): one phase of 41 taps shared by all lanes, held as even- and odd-aligned pairs.
 //       441 -> 320 (22.05 kHz): 320 phases = two hops; even / odd R warps hold the taps of even / odd hops.
 //       anything else: per-sample loop (16 kHz input: plain copy).
@@ -59,7 +63,10 @@ __host__ __device__ constexpr int ws_off22(int r) { return r < 2 ? 0 : r == 2 ? 
 constexpr int WS_LT = 36;                                     // taps per phase (34 non-zero + even alignment)
 constexpr int WS_GROUP_FLOATS = FK_RP * WS_LT;                // 180
 
+// window start of phase r of a group relative to the group's k0, per R-warp class (all even: input pairs stay aligned)
 __host__ __device__ constexpr int ws_off(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 6 : 10; }
+__host__ __device__ constexpr int ws_off1(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 8 : 10; }
+__host__ __device__ constexpr int ws_offc(int cls, int r) { return cls ? ws_off1(r) : ws_off(r); }
 
 // ---- mbarrier / named barrier / register reallocation --------------------------------------------
 __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, unsigned count) {
@@ -100,16 +107,19 @@ __device__ __forceinline__ unsigned long long ws_fma2(unsigned long long a, unsi
   return d;
 }
 
-// One hop of one lane: 5 phases from 46 input samples; T[r][jj] = taps (2jj, 2jj+1) of phase r.   // [phase: ws_resample]
+// One hop of one lane: 5 phases from 46 input samples = 23 aligned 64-bit loads; T[r][jj] = taps (2jj, 2jj+1) of
+// phase r, whose window starts ws_offc(CLS, r) samples after xs.   // [phase: ws_resample]
+template <int CLS>
 __device__ __forceinline__ void ws_resample_hop(const float* __restrict__ xs, const unsigned long long (&T)[FK_RP * WS_LT / 2],
                                                 float (&y)[FK_RP]) {
   unsigned long long acc[FK_RP] = {0ull, 0ull, 0ull, 0ull, 0ull};
+  const unsigned long long* __restrict__ xp2 = reinterpret_cast<const unsigned long long*>(xs);   // 8-byte aligned by construction
 #pragma unroll
-  for (int u = 0; u < ws_off(FK_RP - 1) + WS_LT; u += 2) {
-    const unsigned long long xp = ws_pack(xs[u], xs[u + 1]);
+  for (int u = 0; u < ws_offc(CLS, FK_RP - 1) + WS_LT; u += 2) {
+    const unsigned long long xp = xp2[u >> 1];
 #pragma unroll
     for (int r = 0; r < FK_RP; ++r) {
-      const int j = u - ws_off(r);
+      const int j = u - ws_offc(CLS, r);
       if (j >= 0 && j < WS_LT) acc[r] = ws_fma2(xp, T[r * (WS_LT / 2) + (j >> 1)], acc[r]);
     }
   }
@@ -266,13 +276,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
     unsigned long long TT[FK_RP * WS_LT / 2];
 #pragma unroll
     for (int i = 0; i < FK_RP * WS_LT / 2; ++i) TT[i] = 0ull;
-    int cur_mode = -1, k0 = 0, skew = 0;
+    int cur_mode = -1, k0 = 0;
+    const int cls = rw >> 1;                                     // mode 1: parity class of this warp's tap windows
     if (!MULTI) {                                                // single tuned rate: its taps are loaded once per CTA
-      const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
+      const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + (cls * 32 + g) * WS_GROUP_FLOATS);
 #pragma unroll
       for (int i = 0; i < FK_RP * WS_LT / 2; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
-      k0 = __ldg(fp.ws_k0g + g);
-      skew = ((g - k0) * 9) & 31;
+      k0 = __ldg(fp.ws_k0g + cls * 32 + g);
     }
     int gch = 0;                                                 // chunks this CTA has produced so far
 #ifdef B200_WS_TIMING
@@ -322,11 +332,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       if (MULTI && mode != cur_mode) {
         cur_mode = mode;
         if (mode == 1) {
-          const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + g * WS_GROUP_FLOATS);
+          const float2* tp = reinterpret_cast<const float2*>(fp.ws_taps + (cls * 32 + g) * WS_GROUP_FLOATS);
 #pragma unroll
           for (int i = 0; i < FK_RP * WS_LT / 2; ++i) { const float2 t2 = __ldg(tp + i); TT[i] = ws_pack(t2.x, t2.y); }
-          k0 = __ldg(fp.ws_k0g + g);
-          skew = ((g - k0) * 9) & 31;
+          k0 = __ldg(fp.ws_k0g + cls * 32 + g);
         } else if (MULTI && mode == 2) {
           const float2* tp = reinterpret_cast<const float2*>(fp.ws_t48);
 #pragma unroll
@@ -406,21 +415,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           tc_ = clock64();
           WS_TACC(1, tb_);
 #endif
-          const float* xs = xbuf + sh + k0;
-          if (nh > 8) {
+          // lane g of this class owns the hops q = 2m + pg (m = 0..15) whose window starts on an even address; slot
+          // s = 8 (warp & 1) + i takes m = (s + skew) mod 16 (see the header).  Hops past the chunk's last needed one are
+          // computed from whatever the buffer holds and land in ring rows nobody reads.
+          (void)nh;
+          const int pg = (sh + k0) & 1;
+          const int skew = (9 * ((g & 15) - (((sh + k0 + FK_ORIG * pg) >> 1) & 15))) & 15;
+          const float* xs = xbuf + sh + k0 + pg * FK_ORIG;
+          const int s0 = WS_R_ITERS * (rw & 1) + skew;
+          if (cls == 0) {
 #pragma unroll 1
             for (int i = 0; i < WS_R_ITERS; ++i) {
-              const int q = (WS_R_ITERS * rw + i + skew) & 31;
+              const int q2 = 2 * ((s0 + i) & 15);
               float y[FK_RP];
-              ws_resample_hop(xs + q * FK_ORIG, TT, y);
-              put_hop(rb, slot, q, y);
+              ws_resample_hop<0>(xs + q2 * FK_ORIG, TT, y);
+              put_hop(rb, slot, q2 + pg, y);
             }
-          } else {                                               // short tail chunk: hop = warp, warp + 4
+          } else {
 #pragma unroll 1
-            for (int q = rw; q < nh; q += WS_R_WARPS) {
+            for (int i = 0; i < WS_R_ITERS; ++i) {
+              const int q2 = 2 * ((s0 + i) & 15);
               float y[FK_RP];
-              ws_resample_hop(xs + q * FK_ORIG, TT, y);
-              put_hop(rb, slot, q, y);
+              ws_resample_hop<1>(xs + q2 * FK_ORIG, TT, y);
+              put_hop(rb, slot, q2 + pg, y);
             }
           }
 #ifdef B200_WS_TIMING

@@ -42,6 +42,24 @@ template <int K> struct CS32 {
   static constexpr float s = (q == 0) ? s0 : (q == 1) ? c0 : (q == 2) ? -s0 : -c0;
 };
 
+#ifdef __CUDACC__
+// Packed FP32 pairs on sm_100 (add/sub/mul/fma .f32x2 -> FADD2 / FMUL2 / FFMA2).  Both halves round to nearest like
+// the scalar instructions, so every packed form below is bit-identical to the scalar expression next to it; ptxas
+// folds the half swaps (.LO_HI), per-half sign patterns (.NP / .PN) and scalar broadcasts (.F32) of the pack / unpack
+// moves into operand modifiers, so a complex multiply by a constant is TWO instructions instead of four.
+typedef unsigned long long fx2;
+__device__ __forceinline__ fx2 fx_pk(float lo, float hi) { fx2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 fx_upk(fx2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ fx2 fx_add(fx2 a, fx2 b) { fx2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fx2 fx_sub(fx2 a, fx2 b) { fx2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fx2 fx_mul(fx2 a, fx2 b) { fx2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fx2 fx_fma(fx2 a, fx2 b, fx2 c) { fx2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// (a.x c + a.y s, a.y c - a.x s) = fma((a.y, a.x), (s, -s), (a.x, a.y) * (c, c)): the roundings of the scalar form
+__device__ __forceinline__ float2 fx_cmul_conj(float2 a, float c, float s) {
+  return fx_upk(fx_fma(fx_pk(a.y, a.x), fx_pk(s, -s), fx_mul(fx_pk(a.x, a.y), fx_pk(c, c))));
+}
+#endif
+
 // a * exp(-2*pi*i * K / 32)
 template <int K> B200_HD float2 mul_w32(float2 a) {
   constexpr int k = ((K % 32) + 32) % 32;
@@ -49,6 +67,14 @@ template <int K> B200_HD float2 mul_w32(float2 a) {
   else if constexpr (k == 8) return make_float2(a.y, -a.x);
   else if constexpr (k == 16) return make_float2(-a.x, -a.y);
   else if constexpr (k == 24) return make_float2(-a.y, a.x);
+#ifdef __CUDA_ARCH__
+  // rotations by odd multiples of pi/4: ((a.x + a.y) h, (a.y - a.x) h) etc. as one FADD2 (swap + sign pattern) + one FMUL2
+  else if constexpr (k == 4) { constexpr float h = Cos32<4>::v; return fx_upk(fx_mul(fx_add(fx_pk(a.x, a.y), fx_pk(a.y, -a.x)), fx_pk(h, h))); }
+  else if constexpr (k == 12) { constexpr float h = Cos32<4>::v; return fx_upk(fx_mul(fx_sub(fx_pk(a.y, -a.x), fx_pk(a.x, a.y)), fx_pk(h, h))); }
+  else if constexpr (k == 20) { constexpr float h = Cos32<4>::v; return fx_upk(fx_mul(fx_add(fx_pk(a.x, a.y), fx_pk(a.y, -a.x)), fx_pk(-h, -h))); }
+  else if constexpr (k == 28) { constexpr float h = Cos32<4>::v; return fx_upk(fx_mul(fx_sub(fx_pk(a.x, a.y), fx_pk(a.y, -a.x)), fx_pk(h, h))); }
+  else { return fx_cmul_conj(a, CS32<k>::c, CS32<k>::s); }
+#else
   else if constexpr (k == 4) { constexpr float h = Cos32<4>::v; return make_float2((a.x + a.y) * h, (a.y - a.x) * h); }
   else if constexpr (k == 12) { constexpr float h = Cos32<4>::v; return make_float2((a.y - a.x) * h, -(a.x + a.y) * h); }
   else if constexpr (k == 20) { constexpr float h = Cos32<4>::v; return make_float2(-(a.x + a.y) * h, (a.x - a.y) * h); }
@@ -56,12 +82,9 @@ template <int K> B200_HD float2 mul_w32(float2 a) {
   else {
     constexpr float c = CS32<k>::c, s = CS32<k>::s;
     // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
-#ifdef __CUDA_ARCH__
-    return make_float2(fmaf(a.y, s, a.x * c), fmaf(-a.x, s, a.y * c));
-#else
     return make_float2(std::fmaf(a.y, s, a.x * c), std::fmaf(-a.x, s, a.y * c));
-#endif
   }
+#endif
 }
 
 template <int N> struct BitRev;   // bit reversal of I over log2(N) bits
