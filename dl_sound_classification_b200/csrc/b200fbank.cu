@@ -23,6 +23,7 @@
 #include "fbank_fast.cuh"
 #include "fbank_ws.cuh"
 #include "mixup.cuh"
+#include "clip_norm.cuh"
 #include "patch_embed.cuh"
 #include <cstdlib>
 
@@ -152,7 +153,9 @@ struct b200fbank_plan {
   // warp-specialised kernel (fbank_ws.cuh); shares FastParams
   bool ws_ok = false;
   size_t ws_smem = 0;
-  int* ws_counters = nullptr;   // kWsCounters zero-initialised ints: work counters of dynamic persistent launches (one per launch in flight)
+  // debugging override, read ONCE when the plan is created (never on the launch path): B200FBANK_PERSIST = the
+  // work-distribution mode of the warp-specialised kernel (-1 = unset)
+  int env_persist = -1;
 };
 
 namespace {
@@ -399,7 +402,6 @@ static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin
   }
 }
 
-constexpr int kWsCounters = 64;
 
 int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   using namespace b200;
@@ -628,13 +630,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     // rates without the 44.1 kHz structure still run through this kernel's per-sample path
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;
-    {
-      void* d = nullptr;
-      CUDA_TRY(cudaMalloc(&d, kWsCounters * sizeof(int)));
-      CUDA_TRY(cudaMemset(d, 0, kWsCounters * sizeof(int)));
-      owned.push_back(d);
-      p->ws_counters = (int*)d;
-    }
+    if (const char* e = getenv("B200FBANK_PERSIST")) p->env_persist = atoi(e);
     f.ws_multi = 0;
     for (int i = 0; i < B200_MAX_RATES; ++i) f.ws_multi |= (f.ws_mode[i] >= 2);
 #define B200_WS_ATTR(S, A, M) CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<S, A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin))
@@ -739,18 +735,25 @@ int ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastPa
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     sms = n;
   }
-  const char* env = getenv("B200FBANK_PERSIST");
   int mode = d_offsets == nullptr ? 1 : 2;           // dense: static stride; ragged: dynamic claims
-  if (env) mode = atoi(env);
-  if (mode == 2 && !p->ws_counters) mode = 0;
+  if (p->env_persist >= 0) mode = p->env_persist;
   f.ws_persist = (mode != 0 && grid > sms) ? mode : 0;
   f.ws_counter = nullptr;
   if (f.ws_persist) grid = sms;
   if (f.ws_persist == 2) {
-    static std::atomic<unsigned> seq{0};
-    f.ws_counter = p->ws_counters + (seq.fetch_add(1) % kWsCounters);
+    // one work counter PER LAUNCH from the stream-ordered pool: it is released (ws_release_counter) behind the kernel
+    // on the same stream, so launches in flight on any number of streams never share one
+    void* d = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d, sizeof(int), st));
+    f.ws_counter = (int*)d;
     CUDA_TRY(cudaMemsetAsync(f.ws_counter, 0, sizeof(int), st));
   }
+  return 0;
+}
+
+int ws_release_counter(b200::FastParams& f, cudaStream_t st) {
+  if (f.ws_counter) CUDA_TRY(cudaFreeAsync(f.ws_counter, st));
+  f.ws_counter = nullptr;
   return 0;
 }
 
@@ -814,7 +817,7 @@ int64_t b200fbank_resampled_length(const b200fbank_plan* p, int64_t n, int rate_
 int64_t b200fbank_num_frames(const b200fbank_plan* p, int64_t n, int rate_id) {
   int64_t n_rs = b200fbank_resampled_length(p, n, rate_id);
   if (n_rs < 0) return n_rs;
-  return b200::num_frames(n_rs, p->size, p->shift, p->frame_mode);
+  return b200::num_frames(n_rs, p->size, p->shift, p->frame_mode, p->padded);
 }
 
 int b200fbank_num_cols(const b200fbank_plan* p) { return p ? p->n_cols : fail(B200FBANK_ERR_INVALID, "plan is NULL"); }
@@ -882,6 +885,7 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
       if (f.ast_bank) b200::fbank_ws_kernel<false, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
       else b200::fbank_ws_kernel<false, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
     }
+    if (int rc = ws_release_counter(f, st)) return rc;
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames);
@@ -918,6 +922,7 @@ int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int6
   if (layout != B200FBANK_LAYOUT_BTF && layout != B200FBANK_LAYOUT_BFT) return fail(B200FBANK_ERR_INVALID, "bad layout %d", layout);
   if (!d_out) return fail(B200FBANK_ERR_INVALID, "d_out is NULL");
   if (to_db && !d_clip_max) return fail(B200FBANK_ERR_INVALID, "d_clip_max ([B] floats of workspace) is NULL");
+  if ((to_db || d_masks) && !d_n_frames) return fail(B200FBANK_ERR_INVALID, "d_n_frames is required with to_db or masks (the per-clip pass reads it)");
   if (!to_db && normalize) return fail(B200FBANK_ERR_INVALID, "normalize requires to_db (the reference normalises dB values)");
   if (B == 0) return 0;
   CUDA_TRY(cudaSetDevice(p->device));
@@ -941,11 +946,43 @@ int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int6
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (to_db || d_masks) {
-    k.masks = d_masks;
-    b200::melspec_finalize_kernel<<<B, 256, 0, st>>>(k, to_db ? (float)p->o.top_db : -1.f, normalize);
+    b200::ClipNormParams q;
+    q.x = d_out; q.n_frames = d_n_frames; q.B = B; q.out_frames = out_frames; q.n_cols = k.n_cols; q.layout = layout;
+    q.clip_max = to_db ? d_clip_max : nullptr; q.top_db = to_db ? (float)p->o.top_db : -1.f; q.normalize = normalize;
+    q.target_mean = target_mean; q.target_std = target_std; q.masks = d_masks;
+    b200::clip_normalize_kernel<<<B, b200::CN_THREADS, 0, st>>>(q);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
   }
+  return 0;
+}
+
+int b200fbank_clip_normalize(float* d_x, const int32_t* d_n_frames, int B, int out_frames, int n_cols, int layout,
+                             const float* d_clip_max, float top_db, int normalize, float target_mean, float target_std,
+                             const int32_t* d_masks, void* stream) {
+  if (B < 0 || out_frames <= 0 || n_cols <= 0) return fail(B200FBANK_ERR_INVALID, "bad shape");
+  if (layout != B200FBANK_LAYOUT_BTF && layout != B200FBANK_LAYOUT_BFT) return fail(B200FBANK_ERR_INVALID, "bad layout %d", layout);
+  if (B == 0) return 0;
+  if (!d_x || !d_n_frames) return fail(B200FBANK_ERR_INVALID, "d_x and d_n_frames must not be NULL");
+  b200::ClipNormParams q;
+  q.x = d_x; q.n_frames = d_n_frames; q.B = B; q.out_frames = out_frames; q.n_cols = n_cols; q.layout = layout;
+  q.clip_max = d_clip_max; q.top_db = d_clip_max ? top_db : -1.f; q.normalize = normalize;
+  q.target_mean = target_mean; q.target_std = target_std; q.masks = d_masks;
+  b200::clip_normalize_kernel<<<B, b200::CN_THREADS, 0, (cudaStream_t)stream>>>(q);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200fbank_remove_clip_mean(const float* d_wav, const int64_t* d_offsets, int64_t clip_samples, int B, float* d_out,
+                               float* d_mean, void* stream) {
+  if (B < 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0");
+  if (B == 0) return 0;
+  if (!d_wav || !d_out) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
+  if (!d_offsets && clip_samples <= 0) return fail(B200FBANK_ERR_INVALID, "clip_samples must be > 0 when d_offsets is NULL");
+  b200::clip_mean_kernel<<<B, b200::CN_THREADS, 0, (cudaStream_t)stream>>>(d_wav, d_offsets, clip_samples, d_out, d_mean);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -976,6 +1013,7 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
       if (f.ast_bank) b200::fbank_ws_kernel<true, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
       else b200::fbank_ws_kernel<true, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
     }
+    if (int rc = ws_release_counter(f, (cudaStream_t)stream)) return rc;
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, max_frames);
@@ -1038,12 +1076,11 @@ int b200fbank_mixup(const float* d_x, const float* d_bank, const int32_t* d_part
   if (B < 0 || clip_elems <= 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0 and clip_elems > 0");
   if (B == 0) return 0;
   if (!d_x || !d_bank || !d_partner || !d_lam || !d_out) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
-  if (B > 65535) return fail(B200FBANK_ERR_INVALID, "B = %d exceeds the grid limit 65535 of the mixup launch", B);
   const int64_t per_cta = (int64_t)b200::MIX_THREADS * b200::MIX_VEC_PER_THREAD * 4;
   const int64_t tiles = (clip_elems + per_cta - 1) / per_cta;
-  if (tiles > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "clip_elems too large");
-  b200::mixup_kernel<<<dim3((unsigned)tiles, (unsigned)B), b200::MIX_THREADS, 0, (cudaStream_t)stream>>>(
-      d_x, d_bank, d_partner, d_lam, clip_elems, d_out);
+  if (tiles * B > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit (2^31 - 1 CTAs)");
+  b200::mixup_kernel<<<(unsigned)(tiles * B), b200::MIX_THREADS, 0, (cudaStream_t)stream>>>(
+      d_x, d_bank, d_partner, d_lam, clip_elems, (int)tiles, d_out);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1081,13 +1118,14 @@ int b200fbank_patch_embed(const float* d_feat, int B, int F, int T, const void* 
   const int64_t m_tiles = (k.M + b200::PE_M - 1) / b200::PE_M;
   int per_col = (int)std::min<int64_t>(m_tiles, std::max(1, sms / NT));
   const unsigned grid = (unsigned)(per_col * NT);
-  if (out_f16) {
+  static std::atomic<unsigned long long> attr_done{0};          // bit d: the opt-in shared-memory size is set on device d
+  if (dev >= 64 || !((attr_done.load() >> dev) & 1ull)) {
     CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PE_SMEM));
-    b200::patch_embed_kernel<true><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
-  } else {
     CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PE_SMEM));
-    b200::patch_embed_kernel<false><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
+    if (dev < 64) attr_done.fetch_or(1ull << dev);
   }
+  if (out_f16) b200::patch_embed_kernel<true><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
+  else b200::patch_embed_kernel<false><<<grid, b200::PE_THREADS, b200::PE_SMEM, (cudaStream_t)stream>>>(k);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;

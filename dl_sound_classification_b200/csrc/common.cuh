@@ -67,10 +67,13 @@ __host__ __device__ inline int64_t resampled_length(int64_t n, int orig, int nw)
 
 // Framing modes.  0: kaldi snip_edges=True; 1: kaldi snip_edges=False (mirrored edges, kaldi.py:70-80);
 // 2: torch.stft(center=True, pad_mode="reflect") as used by MelSpectrogram (torchaudio/functional/functional.py:123-137).
-__host__ __device__ inline int64_t num_frames(int64_t n, int size, int shift, int frame_mode) {
+// `padded` (the FFT length) bounds the clips the mirrored framings accept: torch's reflect padding needs
+// n > n_fft / 2 (torch.stft raises otherwise) and kaldi's mirrored left edge needs n >= size/2 - shift/2 samples to
+// mirror; shorter clips yield NO frames here (a batch cannot raise per clip) instead of reading outside the clip.
+__host__ __device__ inline int64_t num_frames(int64_t n, int size, int shift, int frame_mode, int padded = 0) {
   if (frame_mode == 0) return n < size ? 0 : 1 + (n - size) / shift;     // _get_strided, kaldi.py:63-69
-  if (frame_mode == 1) return (n + shift / 2) / shift;
-  return 1 + n / shift;                                                  // stft: 1 + floor((n + 2*(n_fft/2) - n_fft) / hop)
+  if (frame_mode == 1) return n < size / 2 - shift / 2 ? 0 : (n + shift / 2) / shift;
+  return n <= padded / 2 ? 0 : 1 + n / shift;                            // stft: 1 + floor((n + 2*(n_fft/2) - n_fft) / hop)
 }
 
 // First (virtual) sample of frame 0.  Mode 2: the win_length window sits in the middle of the n_fft buffer, so its

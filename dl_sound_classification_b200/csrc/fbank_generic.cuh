@@ -27,7 +27,7 @@ __device__ inline ClipInfo clip_info(const FbankParams& p, int b) {
   int r = p.rate_id ? p.rate_id[b] : 0;
   c.R = p.rates[r];
   c.n_rs = c.R.identity ? c.n_in : resampled_length(c.n_in, c.R.orig, c.R.nw);
-  c.m = num_frames(c.n_rs, p.size, p.shift, p.frame_mode);
+  c.m = num_frames(c.n_rs, p.size, p.shift, p.frame_mode, p.padded);
   return c;
 }
 
@@ -306,65 +306,6 @@ __global__ void fbank_generic_kernel(const FbankParams p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if (lane == 0 && vmax > -INFINITY) atomic_max_float(p.clip_max + b, vmax);
-  }
-}
-
-// AmplitudeToDB(top_db) clamp + the reference's per-clip normalisation (src/datasets/preprocessing.py:1027-1037;
-// torchaudio/functional/functional.py:398-402), in place on the dB values the main kernel wrote.  One CTA per
-// clip: clamp to (clip max - top_db) while summing in float64, then (x - mean) / unbiased_std * target_std +
-// target_mean (skipped when std == 0), SpecAugment zero-fill last.
-__global__ void melspec_finalize_kernel(const FbankParams p, float top_db, int normalize) {
-  __shared__ double red[2][32];
-  __shared__ float s_mu, s_inv;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const ClipInfo c = clip_info(p, b);
-  const int m_eff = (int)(c.m < p.out_frames ? c.m : p.out_frames);
-  float* o = p.out + (size_t)b * p.out_frames * p.n_cols;
-  const size_t st_t = p.layout == 0 ? p.n_cols : 1, st_c = p.layout == 0 ? 1 : p.out_frames;
-  const float floor_db = (top_db >= 0.f && p.clip_max) ? p.clip_max[b] - top_db : -INFINITY;
-  const int ncell = m_eff * p.n_cols;
-  double s = 0.0, ss = 0.0;
-  for (int idx = tid; idx < ncell; idx += blockDim.x) {
-    const int t = p.layout == 0 ? idx / p.n_cols : idx % m_eff;
-    const int col = p.layout == 0 ? idx - t * p.n_cols : idx / m_eff;
-    float* q = o + t * st_t + col * st_c;
-    const float x = fmaxf(*q, floor_db);
-    *q = x;
-    s += (double)x; ss += (double)x * (double)x;
-  }
-#pragma unroll
-  for (int k = 16; k > 0; k >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, k); ss += __shfl_xor_sync(0xffffffffu, ss, k); }
-  if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
-  __syncthreads();
-  if (tid == 0) {
-    double S = 0.0, SS = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { S += red[0][w]; SS += red[1][w]; }
-    const double n = (double)ncell;
-    const double mu = n > 0 ? S / n : 0.0;
-    const double var = n > 1 ? (SS - n * mu * mu) / (n - 1.0) : 0.0;      // torch .std(): unbiased
-    const double sd = var > 0 ? sqrt(var) : 0.0;
-    s_mu = (float)mu;
-    s_inv = (normalize && sd > 0.0) ? (float)(1.0 / sd) : 0.f;
-  }
-  __syncthreads();
-  int mk_local[4];
-  const int* mk = nullptr;
-  if (p.masks) {
-    for (int i = 0; i < 4; ++i) mk_local[i] = __ldg(p.masks + (size_t)b * 4 + i);
-    mk = mk_local;
-  }
-  const bool do_norm = s_inv > 0.f;
-  if (!do_norm && !mk) return;
-  const float mu = s_mu, inv = s_inv;
-  const int nall = p.out_frames * p.n_cols;
-  for (int idx = tid; idx < nall; idx += blockDim.x) {
-    const int t = p.layout == 0 ? idx / p.n_cols : idx % p.out_frames;
-    const int col = p.layout == 0 ? idx - t * p.n_cols : idx / p.out_frames;
-    float* q = o + t * st_t + col * st_c;
-    float x = *q;
-    if (do_norm) x = (x - mu) * inv * p.target_std + p.target_mean;
-    if (mk && ((t >= mk[0] && t < mk[0] + mk[1]) || (col >= mk[2] && col < mk[2] + mk[3]))) x = 0.f;
-    *q = x;
   }
 }
 

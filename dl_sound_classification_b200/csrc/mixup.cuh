@@ -16,11 +16,13 @@ namespace b200 {
 constexpr int MIX_THREADS = 256;
 constexpr int MIX_VEC_PER_THREAD = 4;          // float4 per thread: 4 independent 16-B loads per stream in flight
 
-// grid = (tiles per clip, B).  partner[i] < 0: sample i is not mixed (spec returned unchanged, one-hot label).
+// grid = B * tiles CTAs, clip-major (a linear grid: B is not bound by the 65 535 limit of gridDim.y).
+// partner[i] < 0: sample i is not mixed (spec returned unchanged, one-hot label).
 __global__ void __launch_bounds__(MIX_THREADS) mixup_kernel(const float* __restrict__ x, const float* __restrict__ bank,
                                                             const int32_t* __restrict__ partner, const float* __restrict__ lam,
-                                                            int64_t clip_elems, float* __restrict__ out) {
-  const int i = blockIdx.y;
+                                                            int64_t clip_elems, int tiles, float* __restrict__ out) {
+  const int i = (int)(blockIdx.x / (unsigned)tiles);
+  const int tile = (int)(blockIdx.x - (unsigned)i * (unsigned)tiles);
   const int j = __ldg(partner + i);
   const float l = __ldg(lam + i);
   const float oml = __fsub_rn(1.0f, l);
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(MIX_THREADS) mixup_kernel(const float* __restr
   const float* b = bank + (size_t)(j < 0 ? 0 : j) * clip_elems;
   float* o = out + (size_t)i * clip_elems;
   const int64_t nvec = clip_elems >> 2;
-  const int64_t v0 = ((int64_t)blockIdx.x * MIX_VEC_PER_THREAD) * MIX_THREADS + threadIdx.x;
+  const int64_t v0 = ((int64_t)tile * MIX_VEC_PER_THREAD) * MIX_THREADS + threadIdx.x;
   if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)o) & 15) == 0) {
     float4 va[MIX_VEC_PER_THREAD], vb[MIX_VEC_PER_THREAD];
 #pragma unroll
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(MIX_THREADS) mixup_kernel(const float* __restr
       }
     }
     // tail (clip_elems not a multiple of 4): first tile only
-    if (blockIdx.x == 0 && threadIdx.x < (clip_elems & 3)) {
+    if (tile == 0 && threadIdx.x < (clip_elems & 3)) {
       const int64_t e = (nvec << 2) + threadIdx.x;
       o[e] = j >= 0 ? __fadd_rn(__fmul_rn(l, a[e]), __fmul_rn(oml, b[e])) : a[e];
     }

@@ -7,7 +7,8 @@ path runs in ``libb200fbank.so``.
 from __future__ import annotations
 
 import threading
-from typing import Dict, Optional, Sequence, Tuple, Union
+import weakref
+from typing import Optional, Sequence, Tuple, Union
 
 import torch
 
@@ -24,8 +25,19 @@ _KALDI_DEFAULTS = dict(
 AST_FBANK_KWARGS = dict(htk_compat=True, sample_frequency=16000.0, use_energy=False, window_type="hanning",
                         num_mel_bins=128, frame_shift=10.0)
 
-_plans: Dict[int, "FbankFrontend"] = {}
+# plan id -> frontend, for the torch custom operators (ops.py pass the id, not the object).  Weak references: a frontend
+# (and its device tables) lives exactly as long as its owner keeps it.
+_plans: "weakref.WeakValueDictionary[int, FbankFrontend]" = weakref.WeakValueDictionary()
 _plans_lock = threading.Lock()
+_next_plan_id = [1]
+
+
+def _register(fe: "FbankFrontend") -> int:
+    with _plans_lock:
+        pid = _next_plan_id[0]
+        _next_plan_id[0] += 1
+        _plans[pid] = fe
+    return pid
 
 
 def _require_cuda(device) -> torch.device:
@@ -86,9 +98,7 @@ class FbankFrontend:
             self.device = _require_cuda(device)
             self.plan = K.Plan(opts, self.device.index)
         self.n_cols = self.plan.n_cols
-        with _plans_lock:
-            self.plan_id = (max(_plans) + 1) if _plans else 1
-            _plans[self.plan_id] = self
+        self.plan_id = _register(self)
 
     # -- host arithmetic ---------------------------------------------------------------
     def num_frames(self, n_samples: int, rate_id: int = 0) -> int:
@@ -143,20 +153,32 @@ class FbankFrontend:
                  rate_ids: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None,
                  mean: Union[None, float, torch.Tensor] = None, std: Union[None, float, torch.Tensor] = None,
                  target_mean: float = 0.0, target_std: float = 0.5, layout: str = "btf",
-                 out: Optional[torch.Tensor] = None, return_n_frames: bool = True
-                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                 out: Optional[torch.Tensor] = None, return_n_frames: bool = True, per_clip_norm: bool = False,
+                 remove_clip_mean: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """The fused path (``b200fbank_execute``).  ``mean``/``std``: None (no
         normalisation), scalar, or per-column ``[n_cols]``; output
         ``(x-mean)/std*target_std+target_mean``.  ``masks``: int32 ``(B, 4)`` =
-        ``t_start, t_len, f_start, f_len``; cells zeroed after normalisation."""
+        ``t_start, t_len, f_start, f_len``; cells zeroed after normalisation.
+        ``per_clip_norm``: every clip is normalised with its OWN mean / unbiased std over its real frames instead
+        (``b200fbank_clip_normalize``, the reference's src/datasets/preprocessing.py:1030-1037), masks after it.
+        ``remove_clip_mean``: ``waveform - waveform.mean()`` per clip before the resampler
+        (``b200fbank_remove_clip_mean``; the AST recipe's convention)."""
         wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
+        if per_clip_norm and mean is not None:
+            raise ValueError("per_clip_norm uses each clip's own statistics: do not pass mean/std")
+        if remove_clip_mean and B > 0:
+            centred = torch.empty_like(wav)
+            with torch.cuda.device(self.device):
+                K.check(K.lib.b200fbank_remove_clip_mean(wav.data_ptr(), self._ptr(off), clip, B, centred.data_ptr(), None,
+                                                         torch.cuda.current_stream(self.device).cuda_stream))
+            wav = centred
         lay = {"btf": K.LAYOUT_BTF, "bft": K.LAYOUT_BFT}[layout]
         shape = (B, int(out_frames), self.n_cols) if lay == K.LAYOUT_BTF else (B, 1, self.n_cols, int(out_frames))
         if out is None:
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous float32 {shape} tensor on {self.device}")
-        nfr = torch.empty(B, dtype=torch.int32, device=self.device) if return_n_frames else None
+        nfr = torch.empty(B, dtype=torch.int32, device=self.device) if (return_n_frames or per_clip_norm) else None
         mk = self._dev(masks, torch.int32, "masks")
         if mk is not None and tuple(mk.shape) != (B, 4):
             raise ValueError("masks must be (B, 4) int32: t_start, t_len, f_start, f_len")
@@ -173,10 +195,14 @@ class FbankFrontend:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             K.check(K.lib.b200fbank_execute(
-                self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B, self._ptr(mk),
+                self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B,
+                None if per_clip_norm else self._ptr(mk),
                 self._ptr(mt), self._ptr(st), n_stats, float(target_mean), float(target_std), int(out_frames), lay,
                 out.data_ptr(), self._ptr(nfr), stream))
-        return out, nfr
+            if per_clip_norm and B > 0:
+                K.check(K.lib.b200fbank_clip_normalize(out.data_ptr(), nfr.data_ptr(), B, int(out_frames), self.n_cols, lay,
+                                                       None, -1.0, 1, float(target_mean), float(target_std), self._ptr(mk), stream))
+        return out, (nfr if return_n_frames else None)
 
     def process_host(self, h_wav: torch.Tensor, out_frames: int, h_out: Optional[torch.Tensor] = None,
                      chunk_clips: int = 64, n_streams: int = 3, layout: str = "btf", **kw) -> torch.Tensor:
@@ -289,9 +315,7 @@ class MelSpecFrontend(FbankFrontend):
             self.device = _require_cuda(device)
             self.plan = K.Plan(opts, self.device.index)
         self.n_cols = self.plan.n_cols
-        with _plans_lock:
-            self.plan_id = (max(_plans) + 1) if _plans else 1
-            _plans[self.plan_id] = self
+        self.plan_id = _register(self)
 
     def __call__(self, wav: torch.Tensor, out_frames: int, offsets: Optional[torch.Tensor] = None,
                  rate_ids: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None, to_db: bool = True,
@@ -304,7 +328,7 @@ class MelSpecFrontend(FbankFrontend):
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous float32 {shape} tensor on {self.device}")
-        nfr = torch.empty(B, dtype=torch.int32, device=self.device) if return_n_frames else None
+        nfr = torch.empty(max(B, 1), dtype=torch.int32, device=self.device)[:B]      # the per-clip pass reads it
         mk = self._dev(masks, torch.int32, "masks")
         if mk is not None and tuple(mk.shape) != (B, 4):
             raise ValueError("masks must be (B, 4) int32: t_start, t_len, f_start, f_len")
@@ -314,8 +338,8 @@ class MelSpecFrontend(FbankFrontend):
             K.check(K.lib.b200fbank_melspec_db(
                 self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B, self._ptr(mk),
                 int(bool(to_db)), int(bool(normalize)), float(target_mean), float(target_std), int(out_frames), lay,
-                out.data_ptr(), self._ptr(nfr), cmax.data_ptr(), stream))
-        return out, nfr
+                out.data_ptr(), nfr.data_ptr(), cmax.data_ptr(), stream))
+        return out, (nfr if return_n_frames else None)
 
 
 def launch_count(reset: bool = False) -> int:

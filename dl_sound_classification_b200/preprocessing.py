@@ -253,31 +253,11 @@ class ASTPreprocessor(BasePreprocessor):
         mean = std = None
         if self.normalize and self.norm_mean is not None:
             mean, std = self.norm_mean, self.norm_std
-        per_clip = self.normalize and self.norm_mean is None
-        out, nfr = fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids,
-                      masks=None if per_clip else masks, mean=mean, std=std, target_mean=self.target_mean,
-                      target_std=self.target_std, layout="bft")
-        if per_clip:
-            out = self._per_clip_normalize(out, nfr)
-            if masks is not None:
-                m = masks.to(out.device)
-                for i in range(out.shape[0]):
-                    out[i] = _sa.apply_intervals(out[i], m[i].tolist())
-        return out, nfr
-
-    def _per_clip_normalize(self, x: torch.Tensor, nfr: torch.Tensor) -> torch.Tensor:
-        """The reference's per-clip statistics (src/datasets/preprocessing.py:1030-1037): global mean and
-        UNBIASED std over the clip's own frames, skipped when std == 0."""
-        out = x.clone()
-        for i in range(x.shape[0]):
-            m = int(nfr[i])
-            v = x[i, :, :, :m]
-            if v.numel() < 2:
-                continue
-            mu, sd = v.mean(), v.std()
-            if float(sd) > 0:
-                out[i, :, :, :m] = (v - mu) / sd * self.target_std + self.target_mean
-        return out
+        # without dataset statistics the reference normalises every clip with its OWN mean / unbiased std
+        # (src/datasets/preprocessing.py:1030-1037): one more kernel pass on the device, masks after it
+        per_clip = bool(self.normalize and self.norm_mean is None)
+        return fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids, masks=masks, mean=mean, std=std,
+                  target_mean=self.target_mean, target_std=self.target_std, layout="bft", per_clip_norm=per_clip)
 
     def preprocess(self, waveform: torch.Tensor, sample_rate: int) -> torch.Tensor:
         if waveform.dim() == 1:

@@ -173,13 +173,32 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
  * -> AmplitudeToDB(top_db) -> per-clip (x - mean) / unbiased_std * target_std + target_mean.  Replaces
  * ASTPreprocessor.preprocess (src/datasets/preprocessing.py:1013-1039) and melspectrogram()
  * (src/utils/audio.py:60-84).  to_db = 0 returns the raw mel power (log_scale=False); normalize = 0 skips
- * the per-clip normalisation.  d_clip_max: [B] floats of workspace (receives each clip's dB maximum).
- * Output rows past a clip's frame count (1 + n/hop) hold 0.0.
+ * the per-clip normalisation.  d_clip_max: [B] floats of workspace (receives each clip's dB maximum); d_n_frames is
+ * required with to_db or masks (the per-clip pass reads it).  Output rows past a clip's frame count (1 + n/hop) hold
+ * 0.0; clips of at most n_fft/2 samples (torch.stft's reflect padding raises for them) produce no frames.
  */
 int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
                          int64_t clip_samples, const int32_t* d_rate_id, int B, const int32_t* d_masks,
                          int to_db, int normalize, float target_mean, float target_std, int out_frames,
                          int layout, float* d_out, int32_t* d_n_frames, float* d_clip_max, void* stream);
+
+/* Per-clip normalisation of features already on the device, in place (the reference's ASTPreprocessor.preprocess,
+   src/datasets/preprocessing.py:1030-1037, applied to a batch): for every clip the global mean and UNBIASED standard
+   deviation over its own d_n_frames[b] x n_cols cells, x = (x - mean) / std * target_std + target_mean (skipped when
+   std == 0 or normalize == 0), then the SpecAugment cells of d_masks (may be NULL) are zeroed as
+   src/datasets/esc50.py:267-273 does after the transform.  d_clip_max ([B], may be NULL) with top_db >= 0 applies
+   AmplitudeToDB's clamp max(x, clip_max - top_db) first (torchaudio/functional/functional.py:398-402).  Rows past a
+   clip's frame count are left as they are (the 0.0 padding).  Used by b200fbank_melspec_db itself and, after
+   b200fbank_execute without statistics, for the kaldi recipe with per-clip statistics.  No plan is needed. */
+int b200fbank_clip_normalize(float* d_x, const int32_t* d_n_frames, int B, int out_frames, int n_cols, int layout,
+                             const float* d_clip_max, float top_db, int normalize, float target_mean, float target_std,
+                             const int32_t* d_masks, void* stream);
+
+/* Whole-clip DC removal of the waveforms, `waveform - waveform.mean()` (the AST recipe's
+   convention before kaldi.fbank): d_out[clip] = d_wav[clip] - mean(d_wav[clip]) per clip, same indexing as
+   b200fbank_execute (d_offsets / clip_samples); d_out may alias d_wav; d_mean ([B], may be NULL) receives the means. */
+int b200fbank_remove_clip_mean(const float* d_wav, const int64_t* d_offsets, int64_t clip_samples, int B, float* d_out,
+                               float* d_mean, void* stream);
 
 /* Dataset-statistics pass (north_star config 4; no reference code): the same fused path
    with the epilogue replaced by float64 accumulation of per-column sum / sum of squares
