@@ -40,10 +40,12 @@ FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 def measured_traffic():
     """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01c_ws_full_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    (profiles/r02_ws_full_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None.  ncu cannot run inside a
+    timed bench, so this is the one figure of the line that is not measured live."""
     try:
         tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r01c_ws_full_metrics.csv")):
+        name = "r02_ws_full_metrics.csv" if os.path.exists(os.path.join(ROOT, "profiles", "r02_ws_full_metrics.csv")) else "r01c_ws_full_metrics.csv"
+        for line in open(os.path.join(ROOT, "profiles", name)):
             f = line.strip().split(",")
             if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -91,6 +93,69 @@ def _cpu_worker(args):
     for i in range(n):
         one(clips[i % len(clips)])
     return time.perf_counter() - t0
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _cpu_single(args):
+    """BASELINE.md section 4 modes 1 and 2: ONE process with `threads` intra-op threads over n clips (run in a child so
+    that the thread setting does not leak into the parent)."""
+    n, threads, actual = args
+    import torch
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    clips = [torch.rand(1, CLIP_SAMPLES, generator=g) * 2 - 1 for _ in range(8)]
+    import torchaudio.compliance.kaldi as kaldi
+    import torchaudio.transforms as T
+    if actual:          # the reference-actual recipe (src/datasets/preprocessing.py:988-998, 1013-1039), restated with torchaudio
+        mel = T.MelSpectrogram(sample_rate=44100, n_fft=1024, win_length=400, hop_length=160, n_mels=128, power=2.0)
+        db = T.AmplitudeToDB(top_db=80)
+
+        def one(w):
+            x = db(mel(w))
+            return (x - x.mean()) / x.std() * 0.5
+    else:
+        rs = T.Resample(44100, 16000)
+
+        def one(w):
+            f = kaldi.fbank(rs(w), htk_compat=True, sample_frequency=16000, use_energy=False,
+                            window_type="hanning", num_mel_bins=128, dither=0.0, frame_shift=10)
+            f = torch.nn.functional.pad(f, (0, 0, 0, OUT_FRAMES - f.shape[0]))
+            return (f - AST_MEAN) / (2 * AST_STD)
+    one(clips[0])
+    t0 = time.perf_counter()
+    for i in range(n):
+        one(clips[i % 8])
+    return n * CLIP_SECONDS / (time.perf_counter() - t0)
+
+
+def cpu_modes(n=40):
+    """audio-s/s of BASELINE.md section 4 modes 1 (1 thread) and 2 (all cores, intra-op) and of the reference-actual recipe
+    (all cores), each over n clips in a forked child; call BEFORE CUDA is initialised."""
+    import multiprocessing as mp
+    import torch  # noqa: F401
+    try:
+        import torchaudio.compliance.kaldi  # noqa: F401
+    except Exception:
+        return None
+    ctx = mp.get_context("fork")
+    cores = os.cpu_count() or 1
+    out = {}
+    with ctx.Pool(1) as pool:
+        out["mode1_1proc_1thread"] = pool.apply(_cpu_single, ((n, 1, False),))
+    with ctx.Pool(1) as pool:
+        out["mode2_1proc_allthreads"] = pool.apply(_cpu_single, ((n, cores, False),))
+    with ctx.Pool(1) as pool:
+        out["reference_actual_melspec_db_allthreads"] = pool.apply(_cpu_single, ((max(8, n // 2), cores, True),))
+    return out
 
 
 def cpu_reference_throughput(clips_per_worker=300, workers=None):
@@ -211,6 +276,9 @@ def run_b200(args, rank, local_rank, world):
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(300)           # before CUDA init: workers are forked
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["mode"] = "3: os.cpu_count() single-thread worker processes (BASELINE.md section 4)"
+        cpu["cpu_model"] = cpu_model()
+        cpu["other_modes_audio_s_per_s"] = cpu_modes(40)
     import torch
     import torch.distributed as dist
     import dl_sound_classification_b200 as b2
@@ -284,8 +352,32 @@ def run_b200(args, rank, local_rank, world):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * CLIP_SECONDS * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e_value = world * B * CLIP_SECONDS / (e2e_ms * 1e-3)
     checksum = float(h_out[0, :498].double().sum())
+
+    # the same call fed with 16-bit PCM host buffers (what an ESC-50 WAV holds): half the host -> device bytes, widened on
+    # the device bit-identically to torchaudio.load's float32 (tests/test_gpu_clip_norm.py)
+    h_pcm = (h_wav * 32767.0).round().to(torch.int16).pin_memory()
+
+    def e2e_pcm_step():
+        fe.process_host(h_pcm, OUT_FRAMES, h_out=h_out, chunk_clips=args.e2e_chunk, mean=mean, std=std)
+
+    for _ in range(2):
+        e2e_pcm_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_pcm_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pcm_ms = float(t.item()) / e2e_steps
+    del h_pcm, h_wav
+
+    extra = run_extras(args, torch, dist, b2, dev, rank, world, barrier) if not args.no_extra else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -307,11 +399,129 @@ def run_b200(args, rank, local_rank, world):
                           kernel_ms=k_ms),
             cpu_baseline=cpu,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * CLIP_SAMPLES * 4,
-                     d2h_bytes_per_step=B * OUT_FRAMES * N_MELS * 4, steps=e2e_steps, checksum=checksum),
+                     d2h_bytes_per_step=B * OUT_FRAMES * N_MELS * 4, steps=e2e_steps, checksum=checksum,
+                     ms_per_step=e2e_ms, h2d_gbs_per_rank=B * CLIP_SAMPLES * 4 / (e2e_ms * 1e-3) / 1e9,
+                     d2h_gbs_per_rank=B * OUT_FRAMES * N_MELS * 4 / (e2e_ms * 1e-3) / 1e9,
+                     host_input="float32 pinned (B, 220500)"),
+            e2e_pcm16=dict(value=world * B * CLIP_SECONDS / (pcm_ms * 1e-3), unit=UNIT, ms_per_step=pcm_ms,
+                           h2d_bytes_per_step=B * CLIP_SAMPLES * 2, d2h_bytes_per_step=B * OUT_FRAMES * N_MELS * 4,
+                           h2d_gbs_per_rank=B * CLIP_SAMPLES * 2 / (pcm_ms * 1e-3) / 1e9,
+                           host_input="int16 PCM pinned (B, 220500), widened on the device (b200fbank_pcm16_to_float)"),
+            extra=extra,
             gpu_launches=launches, clocks=clocks)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, torch, dist, b2, dev, rank, world, barrier):
+    """Short runs of BASELINE.json configs[2], [3], [4] at this world size, carried in the headline line's `extra`
+    object so that the driver's BENCH / SCALE records hold them at every N (all ranks take part; times are the max over
+    ranks).  us8k and sweep are weak scaling (every rank its own batch); stats shards 100 000 clips over the ranks and has
+    the NCCL all-reduce INSIDE the timed span."""
+    import random as _random
+    from dl_sound_classification_b200 import stats as ST
+    peak = measured_peaks()[0]
+
+    def timed(fn, steps, warmup=3):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    mean, std = torch.tensor([AST_MEAN], device=dev), torch.tensor([AST_STD], device=dev)
+    # ---- configs[2]: US8K-shaped ragged batch ------------------------------------------------
+    B8, table = 4096, (22050, 44100, 48000)
+    g = torch.Generator().manual_seed(31 + rank)
+    rid = torch.randint(0, 3, (B8,), generator=g)
+    lens = ((1.0 + 3.0 * torch.rand(B8, generator=g)) * torch.tensor(table)[rid]).long()
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)]).to(dev)
+    flat = torch.rand(int(offsets[-1]), generator=gen, device=dev) * 2 - 1
+    fe8 = b2.FbankFrontend(orig_rates=table, device=dev, **b2.AST_FBANK_KWARGS)
+    _random.seed(77)
+    masks = b2.specaugment.draw_masks(B8, 1024, 128, 192, 48).to(dev)
+    rid_d = rid.int().to(dev)
+    out8 = torch.empty((B8, 1024, N_MELS), device=dev)
+    nfr = fe8(flat, 1024, offsets=offsets, rate_ids=rid_d, masks=masks, mean=mean, std=std, out=out8)[1]
+    ms = timed(lambda: fe8(flat, 1024, offsets=offsets, rate_ids=rid_d, masks=masks, mean=mean, std=std, out=out8,
+                           return_n_frames=False), 20)
+    secs = float((lens.double() / torch.tensor(table, dtype=torch.float64)[rid]).sum())
+    in_bytes = int(lens.sum()) * 4
+    real_rows = int(nfr.sum())
+    out["us8k"] = dict(workload="configs[2]: 4096 ragged clips per GPU (1-4 s @22.05/44.1/48 kHz) -> 1024 frames, SpecAugment masks, mean/std",
+                       ms_per_step=ms, value=world * secs / (ms * 1e-3), unit=UNIT, audio_seconds_per_step=secs,
+                       roofline_frac_padded_rows=(in_bytes + B8 * 1024 * N_MELS * 4) / (ms * 1e-3) / 1e9 / peak,
+                       roofline_frac_real_rows=(in_bytes + real_rows * N_MELS * 4) / (ms * 1e-3) / 1e9 / peak,
+                       real_rows_fraction=real_rows / (B8 * 1024.0))
+    del flat, out8, fe8
+    # ---- configs[3]: dataset statistics, 100 000 clips sharded over the ranks + all-reduce -----
+    total = args.clips
+    lo, hi = ST.shard_bounds(total, rank, world)
+    chunk = 4096
+    fe = b2.FbankFrontend(orig_rates=(44100,), device=dev, **b2.AST_FBANK_KWARGS)
+    wav = torch.rand((chunk, CLIP_SAMPLES), generator=gen, device=dev) * 2 - 1     # one synthetic chunk, re-used (untimed set-up)
+    ds = b2.DatasetStats(fe, OUT_FRAMES)
+    ds.update(wav[:64]); ds.all_reduce()                                           # warm-up (NCCL communicator included)
+    ds = b2.DatasetStats(fe, OUT_FRAMES)
+    barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for c0 in range(lo, hi, chunk):
+        ds.update(wav[:min(chunk, hi - c0)])
+    e1.record()
+    ds.all_reduce()
+    e2.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = ds.finalize()
+    out["stats"] = dict(workload=f"configs[3]: per-bin sum / sum of squares over {total} synthetic ESC-50 clips sharded over {world} GPU(s), "
+                                 f"NCCL all-reduce of 257 doubles inside the timed span",
+                        ms_total=float(t[0]), ms_allreduce=float(t[1]), value=total * CLIP_SECONDS / (float(t[0]) * 1e-3), unit=UNIT,
+                        frames=st.frames, roofline_frac=total * CLIP_SAMPLES * 4 / world / (float(t[0]) * 1e-3) / 1e9 / peak)
+    # ---- configs[4]: batch sweep ------------------------------------------------------------
+    sweep = []
+    out_b = torch.empty((chunk, OUT_FRAMES, N_MELS), device=dev)
+    for B in (64, 256, 1024, 4096, 16384, 65536):
+        nb = min(B, chunk)
+        reps = B // nb
+
+        def step():
+            for _ in range(reps):                                  # > 4096 clips: streamed in 4096-clip launches
+                fe(wav[:nb], OUT_FRAMES, mean=mean, std=std, out=out_b[:nb], return_n_frames=False)
+        ms = timed(step, max(3, 40 // reps))
+        sweep.append(dict(batch_per_gpu=B, ms_per_step=ms, value=world * B * CLIP_SECONDS / (ms * 1e-3),
+                          roofline_frac=B * (CLIP_SAMPLES * 4 + OUT_FRAMES * N_MELS * 4) / (ms * 1e-3) / 1e9 / peak))
+    out["sweep"] = dict(workload="configs[4]: batch 64 .. 65536 clips per GPU (beyond 4096: streamed 4096-clip launches)", unit=UNIT, points=sweep)
+    # ---- per-clip statistics instead of dataset statistics (the reference's own normalisation) ----
+    o1 = out_b[:1024]
+    ms = timed(lambda: fe(wav[:1024], OUT_FRAMES, out=o1, per_clip_norm=True, return_n_frames=False), 20)
+    out["per_clip_norm"] = dict(workload="1024 ESC-50 clips per GPU, kaldi recipe + per-clip mean / unbiased-std normalisation (2 kernels)",
+                                ms_per_step=ms, value=world * 1024 * CLIP_SECONDS / (ms * 1e-3), unit=UNIT)
+    del wav, out_b
+    # ---- SURVEY.md section 8f N1: the reference-actual recipe ------------------------------------
+    Bm = 256
+    wm = torch.rand((Bm, CLIP_SAMPLES), generator=gen, device=dev) * 2 - 1
+    fem = b2.MelSpecFrontend(44100, 1024, 160, 400, N_MELS, 80.0, device=dev)
+    ms = timed(lambda: fem(wm, out_frames=1379), 5)
+    alg = Bm * (CLIP_SAMPLES * 4 + N_MELS * 1379 * 4)
+    out["melspec"] = dict(workload="reference-actual recipe: 256 ESC-50 clips per GPU -> MelSpectrogram(1024/160 @44.1 kHz) + dB + per-clip "
+                                   "normalisation -> (256,1,128,1379)",
+                          ms_per_step=ms, value=world * Bm * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
+                          roofline_frac=alg / (ms * 1e-3) / 1e9 / peak)
+    return out
 
 
 def run_extra(args, rank, local_rank, world):
@@ -473,11 +683,15 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short configs[2..4] runs carried in the line's `extra` object")
     ap.add_argument("--workload", default="esc50", choices=["esc50", "us8k", "stats", "sweep", "mixup", "patch_embed", "melspec"],
                     help="esc50 = the headline line (BASELINE.json configs[1]); the others are documentation runs")
     ap.add_argument("--clips", type=int, default=100000, help="clips of the stats workload")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per pipelined chunk of the host-in/host-out path")
     args = ap.parse_args()
+    if os.environ.get("B200_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit if the run is still going after N s
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200_BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -81,6 +81,8 @@ def _load():
     lib.b200fbank_clip_normalize.restype = C.c_int
     lib.b200fbank_remove_clip_mean.argtypes = [VP, VP, I64, C.c_int, VP, VP, VP]
     lib.b200fbank_remove_clip_mean.restype = C.c_int
+    lib.b200fbank_pcm16_to_float.argtypes = [VP, VP, I64, C.c_int, VP, I64, VP, VP]
+    lib.b200fbank_pcm16_to_float.restype = C.c_int
     lib.b200fbank_stats_accumulate.argtypes = [P, VP, VP, I64, VP, C.c_int, C.c_int, VP, VP]
     lib.b200fbank_stats_accumulate.restype = C.c_int
     lib.b200fbank_resample.argtypes = [P, VP, VP, I64, VP, C.c_int, VP, VP, I64, VP]
@@ -108,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "b200fbank_abi_version", "b200fbank_sizeof_opts", "b200fbank_default_opts", "b200fbank_plan_create", "b200fbank_plan_destroy",
     "b200fbank_last_error", "b200fbank_mixup", "b200fbank_mixup_labels", "b200fbank_patch_embed", "b200fbank_resampled_length", "b200fbank_num_frames", "b200fbank_num_cols",
     "b200fbank_plan_table", "b200fbank_plan_info", "b200fbank_execute", "b200fbank_melspec_db",
-    "b200fbank_stats_accumulate", "b200fbank_clip_normalize", "b200fbank_remove_clip_mean",
+    "b200fbank_stats_accumulate", "b200fbank_clip_normalize", "b200fbank_remove_clip_mean", "b200fbank_pcm16_to_float",
     "b200fbank_resample", "b200fbank_launch_count",
 ]
 

@@ -974,6 +974,23 @@ int b200fbank_clip_normalize(float* d_x, const int32_t* d_n_frames, int B, int o
   return 0;
 }
 
+int b200fbank_pcm16_to_float(const int16_t* d_pcm, const int64_t* d_offsets, int64_t clip_samples, int B,
+                             const float* d_divisor, int64_t max_clip_samples, float* d_out, void* stream) {
+  if (B < 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0");
+  if (B == 0) return 0;
+  if (!d_pcm || !d_out) return fail(B200FBANK_ERR_INVALID, "NULL device pointer");
+  const int64_t longest = d_offsets ? max_clip_samples : clip_samples;
+  if (longest <= 0) return fail(B200FBANK_ERR_INVALID, "clip_samples (dense) or max_clip_samples (ragged) must be > 0");
+  const int64_t per_cta = (int64_t)b200::PCM_THREADS * b200::PCM_PER_THREAD;
+  const int64_t tiles = (longest + per_cta - 1) / per_cta;
+  if (tiles * B > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+  b200::pcm16_to_float_kernel<<<(unsigned)(tiles * B), b200::PCM_THREADS, 0, (cudaStream_t)stream>>>(
+      d_pcm, d_offsets, clip_samples, d_divisor, (int)tiles, d_out);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200fbank_remove_clip_mean(const float* d_wav, const int64_t* d_offsets, int64_t clip_samples, int B, float* d_out,
                                float* d_mean, void* stream) {
   if (B < 0) return fail(B200FBANK_ERR_INVALID, "B must be >= 0");

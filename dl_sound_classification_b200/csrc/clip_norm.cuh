@@ -162,4 +162,36 @@ __global__ void __launch_bounds__(CN_THREADS) clip_mean_kernel(const float* wav,
   for (int64_t i = t0 + tid; i < n; i += CN_THREADS) y[i] = x[i] - mu;
 }
 
+// 16-bit PCM -> float32 waveforms on the device: out = float(pcm) / divisor[clip] (correctly rounded division).
+// divisor = 32768 is what torchaudio.load returns for a 16-bit WAV (src/utils/audio.py:42); divisor = max |pcm| of the
+// clip reproduces, bit for bit, the peak normalisation of scripts/prepare_esc50.py:94-101
+// (wave / wave.abs().max() on the loaded float32 samples: both scalings by 2^-15 are exact, so the quotient is the same).
+// Halves the host -> device bytes of the end-to-end path.  grid = (tiles, B).
+constexpr int PCM_THREADS = 256, PCM_PER_THREAD = 8;
+__global__ void __launch_bounds__(PCM_THREADS) pcm16_to_float_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ offsets,
+                                                                    int64_t clip_samples, const float* __restrict__ divisor,
+                                                                    int tiles, float* __restrict__ out) {
+  const int b = (int)(blockIdx.x / (unsigned)tiles), tile = (int)(blockIdx.x - (unsigned)b * (unsigned)tiles);
+  const int64_t o0 = offsets ? offsets[b] : (int64_t)b * clip_samples;
+  const int64_t n = (offsets ? offsets[b + 1] : o0 + clip_samples) - o0;
+  const float d = divisor ? __ldg(divisor + b) : 32768.f;
+  const int16_t* x = pcm + o0;
+  float* y = out + o0;
+  const int64_t e0 = ((int64_t)tile * PCM_THREADS + threadIdx.x) * PCM_PER_THREAD;
+  if (e0 >= n) return;
+  if (e0 + PCM_PER_THREAD <= n && ((uintptr_t)(x + e0) & 15) == 0 && ((uintptr_t)(y + e0) & 15) == 0) {
+    const int4 v = __ldcs(reinterpret_cast<const int4*>(x + e0));
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float4 a, c;
+    a.x = __fdiv_rn((float)(short)(w[0] & 0xffff), d); a.y = __fdiv_rn((float)(short)(w[0] >> 16), d);
+    a.z = __fdiv_rn((float)(short)(w[1] & 0xffff), d); a.w = __fdiv_rn((float)(short)(w[1] >> 16), d);
+    c.x = __fdiv_rn((float)(short)(w[2] & 0xffff), d); c.y = __fdiv_rn((float)(short)(w[2] >> 16), d);
+    c.z = __fdiv_rn((float)(short)(w[3] & 0xffff), d); c.w = __fdiv_rn((float)(short)(w[3] >> 16), d);
+    reinterpret_cast<float4*>(y + e0)[0] = a;
+    reinterpret_cast<float4*>(y + e0)[1] = c;
+  } else {
+    for (int i = 0; i < PCM_PER_THREAD && e0 + i < n; ++i) y[e0 + i] = __fdiv_rn((float)x[e0 + i], d);
+  }
+}
+
 }  // namespace b200

@@ -594,10 +594,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       }
       const int row0 = (gch % WS_SLOTS) * 32;                    // ring row of the item's first hop
       for (int pp = (int)((wf - gpp) & (WS_F_WARPS - 1)); pp < it.pp_total; pp += WS_F_WARPS) {   // [phase: ws_frame_loop]
+        bool waited = false;                                     // this slot has waited for (at least) its own chunk
         if (pp < it.n_pass) {
           const int t0 = it.row_begin + 4 * pp;
           int n_live = it.m_eff - t0;
           n_live = n_live < 0 ? 0 : (n_live > 4 ? 4 : n_live);
+          waited = n_live > 0;
 #ifdef B200_WS_TIMING
           const long long tf0_ = clock64();
 #endif
@@ -616,7 +618,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);
 #endif
         }
-        if (pp < 8 * it.n_chunks) ws_mbar_arrive(bars + WS_SLOTS + (gch + (pp >> 3)) % WS_SLOTS);   // empty[slot of the pass's own rows]
+        if (pp < 8 * it.n_chunks) {
+          // A slot without live frames (pad rows, or beyond the item's passes) only releases ring rows.  It must not do so
+          // before the R warps have produced its chunk: an early arrival would be counted in the PREVIOUS phase of the
+          // slot's `empty` barrier (the chunk three earlier, whose passes a slower warp may still be running), that phase
+          // would complete one arrival short of its own passes and the R warps would overwrite rows still being read.
+          const int gc = gch + (pp >> 3);
+          if (!waited) ws_mbar_wait(bars + gc % WS_SLOTS, (unsigned)((gc / WS_SLOTS) & 1));
+          ws_mbar_arrive(bars + WS_SLOTS + gc % WS_SLOTS);       // empty[slot of the pass's own rows]
+        }
       }
       if (STATS && wf == 0) st_n += it.n_real;
       gch += it.n_chunks;

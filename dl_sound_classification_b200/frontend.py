@@ -204,12 +204,39 @@ class FbankFrontend:
                                                        None, -1.0, 1, float(target_mean), float(target_std), self._ptr(mk), stream))
         return out, (nfr if return_n_frames else None)
 
+    def pcm16_to_float(self, pcm: torch.Tensor, divisor: Optional[torch.Tensor] = None,
+                       offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``b200fbank_pcm16_to_float``: int16 PCM on the device -> float32 ``pcm / divisor[clip]`` (default 32768 =
+        ``torchaudio.load``; the clip's peak = the normalisation of scripts/prepare_esc50.py:94-101, bit for bit)."""
+        if pcm.dtype != torch.int16:
+            raise TypeError("pcm must be int16")
+        pcm = pcm.to(self.device).contiguous()
+        off = self._dev(offsets, torch.int64, "offsets")
+        if off is None:
+            if pcm.dim() != 2:
+                raise ValueError("dense batches must be (B, n_samples); pass offsets for ragged 1-D input")
+            B, clip, longest = int(pcm.shape[0]), int(pcm.shape[1]), 0
+        else:
+            B, clip = int(off.numel()) - 1, 0
+            longest = int((off[1:] - off[:-1]).max()) if B > 0 else 0
+        dv = self._dev(divisor, torch.float32, "divisor")
+        if dv is not None and dv.numel() != B:
+            raise ValueError("divisor must have one entry per clip")
+        if out is None:
+            out = torch.empty(pcm.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            K.check(K.lib.b200fbank_pcm16_to_float(pcm.data_ptr(), self._ptr(off), clip, B, self._ptr(dv), longest,
+                                                   out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
     def process_host(self, h_wav: torch.Tensor, out_frames: int, h_out: Optional[torch.Tensor] = None,
-                     chunk_clips: int = 64, n_streams: int = 3, layout: str = "btf", **kw) -> torch.Tensor:
+                     chunk_clips: int = 64, n_streams: int = 3, layout: str = "btf",
+                     pcm_divisor: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
         """Host buffers in, host buffers out: the end-to-end form of the fused path.
 
-        ``h_wav`` is a dense ``(B, n_samples)`` float32 CPU tensor (pinned memory for full PCIe
-        speed), the result a CPU tensor (pinned when allocated here).  The batch is cut into
+        ``h_wav`` is a dense ``(B, n_samples)`` CPU tensor (pinned memory for full PCIe speed): float32 waveforms, or
+        int16 PCM (half the host -> device bytes; widened on the device as ``pcm / pcm_divisor[clip]``, default 32768,
+        see ``pcm16_to_float``).  The result is a CPU tensor (pinned when allocated here).  The batch is cut into
         chunks that rotate over ``n_streams`` CUDA streams, so the host->device copy of chunk
         i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
         duplex; the kernel is ~30x faster than either copy).  Keyword arguments are those of
@@ -218,8 +245,10 @@ class FbankFrontend:
         """
         if self.device is None:
             raise K.B200FbankError(K.ERR_NO_DEVICE, "host-only plan: no CPU compute path exists")
-        if h_wav.device.type != "cpu" or h_wav.dim() != 2 or h_wav.dtype != torch.float32:
-            raise ValueError("h_wav must be a dense (B, n_samples) float32 CPU tensor")
+        if h_wav.device.type != "cpu" or h_wav.dim() != 2 or h_wav.dtype not in (torch.float32, torch.int16):
+            raise ValueError("h_wav must be a dense (B, n_samples) float32 or int16 CPU tensor")
+        pcm = h_wav.dtype == torch.int16
+        div = self._dev(pcm_divisor, torch.float32, "pcm_divisor") if pcm else None
         B, N = int(h_wav.shape[0]), int(h_wav.shape[1])
         shape = (B, int(out_frames), self.n_cols) if layout == "btf" else (B, 1, self.n_cols, int(out_frames))
         if h_out is None:
@@ -232,10 +261,12 @@ class FbankFrontend:
                 kw[k] = self._dev(torch.as_tensor(kw[k], dtype=torch.float32).reshape(-1), torch.float32, k)
         chunk_clips = max(1, min(int(chunk_clips), B))
         state = getattr(self, "_host_pipe", None)
-        key = (chunk_clips, N, shape[1:], n_streams)
+        key = (chunk_clips, N, shape[1:], n_streams, pcm)
         if state is None or state["key"] != key:
             state = dict(key=key, streams=[torch.cuda.Stream(self.device) for _ in range(n_streams)],
                          d_wav=[torch.empty((chunk_clips, N), dtype=torch.float32, device=self.device) for _ in range(n_streams)],
+                         d_pcm=[torch.empty((chunk_clips, N), dtype=torch.int16, device=self.device) for _ in range(n_streams)]
+                         if pcm else None,
                          d_out=[torch.empty((chunk_clips,) + shape[1:], dtype=torch.float32, device=self.device)
                                 for _ in range(n_streams)])
             self._host_pipe = state
@@ -248,7 +279,12 @@ class FbankFrontend:
             k = i % n_streams
             with torch.cuda.stream(state["streams"][k]):
                 dw, do = state["d_wav"][k][:n], state["d_out"][k][:n]
-                dw.copy_(h_wav[lo:hi], non_blocking=True)
+                if pcm:
+                    dp = state["d_pcm"][k][:n]
+                    dp.copy_(h_wav[lo:hi], non_blocking=True)
+                    self.pcm16_to_float(dp, None if div is None else div[lo:hi], out=dw)
+                else:
+                    dw.copy_(h_wav[lo:hi], non_blocking=True)
                 self(dw, out_frames, masks=None if masks is None else masks[lo:hi], layout=layout, out=do,
                      return_n_frames=False, **kw)
                 h_out[lo:hi].copy_(do, non_blocking=True)

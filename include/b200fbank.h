@@ -200,6 +200,14 @@ int b200fbank_clip_normalize(float* d_x, const int32_t* d_n_frames, int B, int o
 int b200fbank_remove_clip_mean(const float* d_wav, const int64_t* d_offsets, int64_t clip_samples, int B, float* d_out,
                                float* d_mean, void* stream);
 
+/* 16-bit PCM -> float32 waveforms on the device: d_out = float(d_pcm) / d_divisor[clip] (correctly rounded), same
+   indexing as b200fbank_execute; d_divisor NULL = 32768, i.e. what torchaudio.load returns for a 16-bit WAV
+   (src/utils/audio.py:42); d_divisor[b] = max |pcm| of clip b reproduces scripts/prepare_esc50.py:94-101 (peak
+   normalisation of the loaded samples) bit for bit.  max_clip_samples: the longest clip of a ragged batch (sizes the
+   launch; ignored for dense batches).  Halves the host -> device bytes of the end-to-end path. */
+int b200fbank_pcm16_to_float(const int16_t* d_pcm, const int64_t* d_offsets, int64_t clip_samples, int B,
+                             const float* d_divisor, int64_t max_clip_samples, float* d_out, void* stream);
+
 /* Dataset-statistics pass (north_star config 4; no reference code): the same fused path
    with the epilogue replaced by float64 accumulation of per-column sum / sum of squares
    over the REAL frames [0, min(frames, max_frames)) of every clip.  d_sums is

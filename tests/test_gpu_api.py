@@ -266,6 +266,16 @@ def test_reference_actual_batch_and_masks(b2, O):
     assert np.abs(mine.numpy() - db.numpy()).max() < 5e-3
 
 
+def _frontends_per_launch_form(b2, monkeypatch, flags, **kw):
+    """B200FBANK_PERSIST is read once, when a plan is created: one frontend per launch form."""
+    fes = {}
+    for flag in flags:
+        monkeypatch.setenv("B200FBANK_PERSIST", flag)
+        fes[flag] = b2.FbankFrontend(**kw)
+    monkeypatch.delenv("B200FBANK_PERSIST")
+    return fes
+
+
 @pytest.mark.parametrize("rate,seconds,frames", [(44100, 2.3, 1024), (48000, 1.1, 256), (22050, 0.9, 128), (16000, 1.5, 512)])
 def test_persistent_launch_is_bit_identical_to_one_cta_per_item(b2, O, monkeypatch, rate, seconds, frames):
     """Dense batches larger than one wave run as ONE CTA per SM that walks its items with the resampler / frame pipeline
@@ -276,19 +286,16 @@ def test_persistent_launch_is_bit_identical_to_one_cta_per_item(b2, O, monkeypat
     g = torch.Generator().manual_seed(rate + frames)
     wav = (torch.rand((B, n), generator=g) * 2 - 1).cuda()
     table = (22050, 44100, 48000, 16000)
-    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    fes = _frontends_per_launch_form(b2, monkeypatch, ("1", "0"), orig_rates=table, **b2.AST_FBANK_KWARGS)
     rid = torch.full((B,), table.index(rate), dtype=torch.int32)
     random.seed(5)
     masks = b2.specaugment.draw_masks(B, frames, 128, 48, 24, variant="reference")
     kw = dict(out_frames=frames, rate_ids=rid, masks=masks, mean=AST_MEAN, std=AST_STD)
-    monkeypatch.setenv("B200FBANK_PERSIST", "1")
-    out_p, nfr_p = fe(wav, **kw)
-    monkeypatch.setenv("B200FBANK_PERSIST", "0")
-    out_1, nfr_1 = fe(wav, **kw)
+    out_p, nfr_p = fes["1"](wav, **kw)
+    out_1, nfr_1 = fes["0"](wav, **kw)
     torch.cuda.synchronize()
     assert torch.equal(nfr_p, nfr_1) and torch.equal(out_p, out_1)
-    monkeypatch.setenv("B200FBANK_PERSIST", "1")
-    raw, _ = fe(wav, out_frames=frames, rate_ids=rid)               # un-normalised, un-masked: the oracle's units
+    raw, _ = fes["1"](wav, out_frames=frames, rate_ids=rid)         # un-normalised, un-masked: the oracle's units
     for i in (0, 147, 148, 332):
         ref = O.kaldi_fbank(O.resample(wav[i].cpu().numpy(), rate, 16000), O.ast_fbank_options())
         m = min(ref.shape[0], frames)
@@ -297,8 +304,7 @@ def test_persistent_launch_is_bit_identical_to_one_cta_per_item(b2, O, monkeypat
     # the stats pass takes the same two launch forms (float64 atomics: equal up to summation order)
     sums = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("B200FBANK_PERSIST", flag)
-        ds = b2.DatasetStats(fe, max_frames=frames)
+        ds = b2.DatasetStats(fes[flag], max_frames=frames)
         ds.update(wav, rate_ids=rid)
         sums.append(ds.sums.cpu().numpy())
     assert sums[0][-1] == sums[1][-1] == float(nfr_p.sum().item())
@@ -319,14 +325,14 @@ def test_dynamic_persistent_launch_on_ragged_batches(b2, O, monkeypatch):
     lens[300:310] = 100                                   # shorter than one 25 ms window: zero frames, pad rows only
     offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
     flat = (torch.rand(int(offsets[-1]), generator=g) * 2 - 1).cuda()
+    fes = _frontends_per_launch_form(b2, monkeypatch, ("2", "0"), orig_rates=table, **b2.AST_FBANK_KWARGS)
     fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
     random.seed(9)
     masks = b2.specaugment.draw_masks(B, 128, 128, 32, 16, variant="reference")
     kw = dict(out_frames=128, offsets=offsets, rate_ids=rid.int(), masks=masks, mean=AST_MEAN, std=AST_STD)
     outs = {}
     for flag in ("2", "0", "2"):
-        monkeypatch.setenv("B200FBANK_PERSIST", flag)
-        out, nfr = fe(flat, **kw)
+        out, nfr = fes[flag](flat, **kw)
         torch.cuda.synchronize()
         if flag in outs:
             assert torch.equal(out, outs[flag][0])            # the claim order varies from run to run, the result does not
@@ -336,7 +342,6 @@ def test_dynamic_persistent_launch_on_ragged_batches(b2, O, monkeypatch):
     assert int(nfr[5]) == 0 and bool((nfr[300:310] == 0).all())
     want = [min(128, fe.num_frames(int(n), int(r))) for n, r in zip(lens, rid)]
     assert nfr.tolist() == want
-    monkeypatch.delenv("B200FBANK_PERSIST")
     raw, _ = fe(flat, out_frames=128, offsets=offsets, rate_ids=rid.int())
     for i in (0, 1, 299, 311, 699):
         w = flat[int(offsets[i]):int(offsets[i + 1])].cpu().numpy()
@@ -352,11 +357,11 @@ def test_persistent_launch_with_a_non_ast_filterbank(b2, monkeypatch):
     B, n = 400, 16000 + 123
     g = torch.Generator().manual_seed(77)
     wav = (torch.rand((B, n), generator=g) * 2 - 1).cuda()
-    fe = b2.FbankFrontend(orig_rates=(16000,), num_mel_bins=40, window_type="povey", sample_frequency=16000.0)
+    fes = _frontends_per_launch_form(b2, monkeypatch, ("1", "0"), orig_rates=(16000,), num_mel_bins=40, window_type="povey",
+                                     sample_frequency=16000.0)
     outs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("B200FBANK_PERSIST", flag)
-        outs.append(fe(wav, out_frames=128))
+        outs.append(fes[flag](wav, out_frames=128))
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     m = int(outs[0][1][0])
@@ -378,3 +383,26 @@ def test_process_host_matches_device_call(b2):
             got = fe.process_host(h_wav, 128, chunk_clips=chunk, mean=AST_MEAN, std=AST_STD, layout=layout)
             assert got.device.type == "cpu"
             assert torch.equal(got, want.cpu()), (layout, chunk)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_us8k_shaped_dynamic_launch_is_race_free(b2, monkeypatch, seed):
+    """Regression (round 2): pass slots without live frames used to release their ring rows without waiting for the R
+    warps, so their arrivals could be counted in the previous phase of the slot's `empty` barrier; with US8K-shaped
+    batches (every second segment is padding only) and time masks the resampler then overwrote rows still being read:
+    results differed from one CTA per item and the seed-32 batch deadlocked.  Both launch forms must agree bit for bit."""
+    B, table = 4096, (22050, 44100, 48000)
+    g = torch.Generator().manual_seed(seed)
+    rid = torch.randint(0, 3, (B,), generator=g)
+    lens = ((1.0 + 3.0 * torch.rand(B, generator=g)) * torch.tensor(table)[rid]).long()
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)]).cuda()
+    flat = torch.rand(int(offsets[-1]), device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed + 46)) * 2 - 1
+    random.seed(77)
+    masks = b2.specaugment.draw_masks(B, 1024, 128, 192, 48).cuda()
+    fes = _frontends_per_launch_form(b2, monkeypatch, ("2", "0"), orig_rates=table, **b2.AST_FBANK_KWARGS)
+    kw = dict(out_frames=1024, offsets=offsets, rate_ids=rid.int().cuda(), masks=masks, return_n_frames=False)
+    ref = fes["0"](flat, **kw)[0]
+    for _ in range(3):
+        got = fes["2"](flat, **kw)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref)

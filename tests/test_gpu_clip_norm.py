@@ -104,3 +104,27 @@ def test_mixup_more_than_65535_clips(b2):
     l = lam.cuda()[:, None]
     want = torch.where(partner.cuda()[:, None] >= 0, l * x + (1 - l) * bank[partner.clamp(min=0).long().cuda()], x)
     assert torch.equal(out, want)
+
+
+def test_pcm16_input_is_bit_identical_to_the_float_contract(b2):
+    """int16 PCM + per-clip divisor widened on the device == torchaudio.load's float32 (/32768) followed by the peak
+    normalisation of scripts/prepare_esc50.py:94-101; the end-to-end call gives the same features either way."""
+    g = torch.Generator().manual_seed(9)
+    pcm = torch.randint(-20000, 20000, (5, 44100), generator=g, dtype=torch.int32).to(torch.int16)
+    wave = pcm.to(torch.float32) / 32768.0                                # what torchaudio.load returns
+    peak = wave.abs().amax(dim=1, keepdim=True)
+    norm = wave / peak                                                    # prepare_esc50.py: wave / max|wave|
+    fe = b2.FbankFrontend(orig_rates=(44100,), **b2.AST_FBANK_KWARGS)
+    assert torch.equal(fe.pcm16_to_float(pcm.cuda()).cpu(), wave)
+    div = pcm.to(torch.int32).abs().amax(dim=1).to(torch.float32)
+    assert torch.equal(fe.pcm16_to_float(pcm.cuda(), div).cpu(), norm)
+    a = fe.process_host(norm.pin_memory(), 128, chunk_clips=2, mean=-6.6, std=5.0)
+    b = fe.process_host(pcm.pin_memory(), 128, chunk_clips=2, pcm_divisor=div, mean=-6.6, std=5.0)
+    assert torch.equal(a, b)
+    # ragged form
+    lens = torch.tensor([1000, 7, 44100 - 3, 12345])
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    flat = torch.cat([pcm[i, :int(n)] for i, n in enumerate(lens)])
+    got = fe.pcm16_to_float(flat.cuda(), div[:4], offsets=offs).cpu()
+    want = torch.cat([pcm[i, :int(n)].to(torch.float32) / div[i] for i, n in enumerate(lens)])
+    assert torch.equal(got, want)

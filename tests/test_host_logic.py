@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "b200fbank.h")).read()
-    declared = sorted(set(re.findall(r"\b(b200fbank_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(b200fbank_[a-z0-9_]+)\s*\(", hdr)))
     assert len(declared) >= 15
     lib = ctypes.CDLL(K.LIB_PATH)
     for name in declared:
