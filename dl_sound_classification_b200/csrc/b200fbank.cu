@@ -24,6 +24,7 @@
 #include "fbank_ws.cuh"
 #include "mixup.cuh"
 #include "clip_norm.cuh"
+#include "melspec_fast.cuh"
 #include "patch_embed.cuh"
 #include <cstdlib>
 
@@ -156,6 +157,10 @@ struct b200fbank_plan {
   // debugging override, read ONCE when the plan is created (never on the launch path): B200FBANK_PERSIST = the
   // work-distribution mode of the warp-specialised kernel (-1 = unset)
   int env_persist = -1;
+  // tuned MelSpectrogram-dB kernel (melspec_fast.cuh)
+  int melfast = 0;              // 0: not available, 1: <13, 5> (window <= 416, hop 160), 2: <32, 0> (any window / hop)
+  b200::MelFastParams mfast;
+  size_t mfast_smem = 0;
 };
 
 namespace {
@@ -331,12 +336,12 @@ void generic_smem_layout(const b200fbank_plan* p, int F, int* sy, int* sx, int* 
 // configuration is outside its envelope (the generic kernel then serves every call).
 // Wavefronts of one LDS.128 by a quarter-warp whose lanes read power cells a[0..7] (16 B each, -1 = idle lane):
 // cells in the same 16-B bank group (index mod 8) serialise unless they are the same cell.
-static int quarter_wavefronts(const int* a) {
+static int quarter_wavefronts(const int* a, int nl = 8) {      // nl = 16: one LDS.64 by a half-warp (8-B cells, 16 bank pairs)
   int worst = 1;
-  for (int r = 0; r < 8; ++r) {
-    int seen[8], n = 0;
-    for (int l = 0; l < 8; ++l) {
-      if (a[l] < 0 || (a[l] & 7) != r) continue;
+  for (int r = 0; r < nl; ++r) {
+    int seen[16], n = 0;
+    for (int l = 0; l < nl; ++l) {
+      if (a[l] < 0 || (a[l] & (nl - 1)) != r) continue;
       bool dup = false;
       for (int q = 0; q < n; ++q) dup |= seen[q] == a[l];
       if (!dup) seen[n++] = a[l];
@@ -348,7 +353,7 @@ static int quarter_wavefronts(const int* a) {
 
 // Lane slots of mel group `gi` (bins 32 gi .. 32 gi + 31): a deterministic annealing over (bin permutation, early
 // start of short filters) that minimises the LDS.128 wavefronts of the group's tap loop; identity if nothing better.
-static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin, int* start) {
+static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin, int* start, int nl = 8) {
   int slack[32], sh[32], cell[32];
   for (int l = 0; l < 32; ++l) {
     const int m = 32 * gi + l;
@@ -358,12 +363,12 @@ static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin
   }
   auto cost = [&]() {
     int c = 0;
-    for (int q = 0; q < 4; ++q) {
-      for (int l = 0; l < 8; ++l) {
-        const int m = bin[8 * q + l];
-        cell[l] = m < p->n_mel ? p->mel_start[m] - sh[m - 32 * gi] : -1;
+    for (int q = 0; q < 32 / nl; ++q) {
+      for (int l = 0; l < nl; ++l) {
+        const int m = bin[nl * q + l];
+        cell[l] = (m < p->n_mel && p->mel_cnt[m] > 0) ? p->mel_start[m] - sh[m - 32 * gi] : -1;
       }
-      c += quarter_wavefronts(cell);
+      c += quarter_wavefronts(cell, nl);
     }
     return c;
   };
@@ -372,12 +377,12 @@ static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin
   int cur = cost(), best = cur, best_bin[32], best_sh[32];
   std::copy(bin, bin + 32, best_bin); std::copy(sh, sh + 32, best_sh);
   double T = 1.0;
-  for (int it = 0; it < 60000 && best > 4; ++it, T = std::max(0.05, T * 0.9999)) {
+  for (int it = 0; it < 60000 && best > 32 / nl; ++it, T = std::max(0.05, T * 0.9999)) {
     const int a = (int)(next() & 31), b = (int)(next() & 31);
     const bool swap_move = (next() & 1) != 0;
     int old_sh = 0;
     if (swap_move) {
-      if ((a >> 3) == (b >> 3)) continue;
+      if (a / nl == b / nl) continue;
       std::swap(bin[a], bin[b]);
     } else {
       if (slack[a] == 0) continue;
@@ -402,6 +407,66 @@ static void plan_mel_slots(const b200fbank_plan* p, int gi, int maxcnt, int* bin
   }
 }
 
+
+// Tables of the tuned MelSpectrogram-dB kernel (melspec_fast.cuh): 1024-point transforms at the clips' own rate.
+int setup_melfast(b200fbank_plan* p, std::vector<void*>& owned) {
+  using namespace b200;
+  const b200fbank_opts& o = p->o;
+  p->melfast = 0;
+  const char* env = getenv("B200FBANK_KERNEL");
+  if (env && strcmp(env, "generic") == 0) return 0;
+  if (o.frontend != B200FBANK_FRONTEND_MELSPEC_DB || p->padded != MS_N || p->n_mel > 128 || p->n_mel < 1) return 0;
+  for (const RateHost& r : p->rates)
+    if (!r.identity) return 0;                                   // a clip that needs resampling takes the generic kernel
+  MelFastParams& f = p->mfast;
+  f.groups = (p->n_mel + 31) / 32;
+  int rows = 0;
+  for (int i = 0; i < 4; ++i) { f.maxcnt[i] = 0; f.woff[i] = 0; }
+  for (int i = 0; i < f.groups; ++i) {
+    int mc = 1;
+    for (int m = 32 * i; m < std::min(32 * i + 32, p->n_mel); ++m) mc = std::max(mc, p->mel_cnt[m]);
+    f.maxcnt[i] = mc; f.woff[i] = rows; rows += mc;
+  }
+  f.rows = rows;
+  std::vector<float> tw((size_t)2 * MS_N);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double a = 2.0 * M_PI * (double)(k1 * l) / MS_N;
+      tw[2 * (k1 * 32 + l)] = (float)std::cos(a);
+      tw[2 * (k1 * 32 + l) + 1] = (float)(-std::sin(a));
+    }
+  std::vector<int> slot_bin(32 * f.groups), slot_start(32 * f.groups, 0);
+  for (int i = 0; i < f.groups; ++i) plan_mel_slots(p, i, f.maxcnt[i], slot_bin.data() + 32 * i, slot_start.data() + 32 * i, 16);
+  std::vector<float> melw((size_t)rows * 32, 0.f);
+  for (int i = 0; i < f.groups; ++i)
+    for (int l = 0; l < 32; ++l) {
+      const int m = slot_bin[32 * i + l];
+      if (m >= p->n_mel) continue;
+      const int lead = p->mel_start[m] - slot_start[32 * i + l];
+      for (int j = 0; j < p->mel_cnt[m]; ++j)        // x 1/4: the conjugate split leaves the factor of the power out
+        melw[(size_t)(f.woff[i] + lead + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * 0.25f;
+    }
+  auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    CUDA_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    *dst = d;
+    return 0;
+  };
+  if (p->device >= 0) {
+    if (int rc = dev_copy(tw.data(), tw.size() * 4, (const void**)&f.tw)) return rc;
+    if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
+    if (int rc = dev_copy(slot_bin.data(), slot_bin.size() * 4, (const void**)&f.slot_bin)) return rc;
+    if (int rc = dev_copy(slot_start.data(), slot_start.size() * 4, (const void**)&f.slot_start)) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<13, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  }
+  p->mfast_smem = (size_t)(2 * MS_N + ((rows * 32 + 3) & ~3) + MS_WARPS * (MS_EBUF + MS_TBUF)) * 4;
+  if (p->mfast_smem > (size_t)kMaxSmemOptin) return 0;
+  p->melfast = (p->size <= 13 * 32 && p->shift == 5 * 32) ? 1 : 2;
+  return 0;
+}
 
 int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
   using namespace b200;
@@ -696,6 +761,7 @@ int upload(b200fbank_plan* p) {
   k.mel_w = (const float*)(d + o_mw);
 
   if (int rc = setup_fast(p, blob_host_extra)) return rc;
+  if (int rc = setup_melfast(p, blob_host_extra)) return rc;
 
   // pick the largest tile that fits comfortably (two CTAs per SM when possible)
   int F = 16;
@@ -939,12 +1005,36 @@ int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int6
     b200::fill_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned*>(d_clip_max), kNegInf, B);
     ++g_launches;
   }
-  k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
-  const int64_t grid = (int64_t)B * k.tiles;
-  if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
-  b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  if (p->melfast) {
+    // tuned kernel: independent warps claim 8-frame tiles from a per-launch counter (stream-ordered allocation)
+    b200::MelFastParams f = p->mfast;
+    f.tiles_per_clip = (out_frames + b200::MS_TILE - 1) / b200::MS_TILE;
+    if ((int64_t)B * f.tiles_per_clip > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds 2^31 - 1");
+    void* d = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d, sizeof(int), st));
+    f.counter = (int*)d;
+    CUDA_TRY(cudaMemsetAsync(f.counter, 0, sizeof(int), st));
+    static int sms = 0;
+    if (sms == 0) {
+      int n = 0;
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || n <= 0) n = 148;
+      sms = n;
+    }
+    const int64_t warps_needed = (int64_t)B * f.tiles_per_clip;
+    const int grid = (int)std::min<int64_t>(sms, (warps_needed + b200::MS_WARPS - 1) / b200::MS_WARPS);
+    if (p->melfast == 1) b200::melspec_fast_kernel<13, 5><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+    else b200::melspec_fast_kernel<32, 0><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d, st));
+  } else {
+    k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
+    const int64_t grid = (int64_t)B * k.tiles;
+    if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds the grid limit");
+    b200::fbank_generic_kernel<false><<<(unsigned)grid, p->generic_threads, p->generic_smem, st>>>(k);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   if (to_db || d_masks) {
     b200::ClipNormParams q;
     q.x = d_out; q.n_frames = d_n_frames; q.B = B; q.out_frames = out_frames; q.n_cols = k.n_cols; q.layout = layout;
