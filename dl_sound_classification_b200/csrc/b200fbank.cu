@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -131,6 +132,45 @@ double vtln_warp_freq(double vl, double vh, double lo, double hi, double warp, d
 
 }  // namespace
 
+// Per-launch work counters of the persistent kernels (items / tiles are claimed with atomicAdd).  A ring of device ints,
+// each guarded by an event recorded behind the kernel that used it: a launch takes the first slot whose last user has
+// finished (whatever stream that was on), so launches in flight on any number of streams never share a counter, and
+// the launch path makes no allocation.  (cudaMallocAsync per launch was tried: correct, but the stream-ordered pool
+// cost up to 0.5 ms per launch once other work had synchronised the device.)
+struct CounterRing {
+  static constexpr int kSlots = 64;
+  int* base = nullptr;
+  cudaEvent_t ev[kSlots] = {};
+  bool used[kSlots] = {};
+  int next = 0;
+  std::mutex mu;
+  int init() {
+    if (cudaMalloc((void**)&base, kSlots * sizeof(int)) != cudaSuccess) return -1;
+    for (int i = 0; i < kSlots; ++i)
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+    return 0;
+  }
+  // returns the slot index; the counter is zeroed on `st`
+  int acquire(cudaStream_t st, int** out) {
+    std::lock_guard<std::mutex> lock(mu);
+    int idx = -1;
+    for (int i = 0; i < kSlots && idx < 0; ++i) {
+      const int c = (next + i) % kSlots;
+      if (!used[c] || cudaEventQuery(ev[c]) == cudaSuccess) idx = c;
+    }
+    if (idx < 0) { idx = next; cudaEventSynchronize(ev[idx]); }
+    next = (idx + 1) % kSlots;
+    used[idx] = true;
+    *out = base + idx;
+    return cudaMemsetAsync(base + idx, 0, sizeof(int), st) == cudaSuccess ? idx : -1;
+  }
+  void release(int idx, cudaStream_t st) { if (idx >= 0) cudaEventRecord(ev[idx], st); }
+  ~CounterRing() {
+    for (int i = 0; i < kSlots; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (base) cudaFree(base);
+  }
+};
+
 struct b200fbank_plan {
   b200fbank_opts o;
   int device = -1;
@@ -157,6 +197,7 @@ struct b200fbank_plan {
   // debugging override, read ONCE when the plan is created (never on the launch path): B200FBANK_PERSIST = the
   // work-distribution mode of the warp-specialised kernel (-1 = unset)
   int env_persist = -1;
+  mutable CounterRing counters;
   // tuned MelSpectrogram-dB kernel (melspec_fast.cuh)
   int melfast = 0;              // 0: not available, 1: <13, 5> (window <= 416, hop 160), 2: <32, 0> (any window / hop)
   b200::MelFastParams mfast;
@@ -436,16 +477,106 @@ int setup_melfast(b200fbank_plan* p, std::vector<void*>& owned) {
       tw[2 * (k1 * 32 + l) + 1] = (float)(-std::sin(a));
     }
   std::vector<int> slot_bin(32 * f.groups), slot_start(32 * f.groups, 0);
-  for (int i = 0; i < f.groups; ++i) plan_mel_slots(p, i, f.maxcnt[i], slot_bin.data() + 32 * i, slot_start.data() + 32 * i, 16);
-  std::vector<float> melw((size_t)rows * 32, 0.f);
-  for (int i = 0; i < f.groups; ++i)
-    for (int l = 0; l < 32; ++l) {
-      const int m = slot_bin[32 * i + l];
-      if (m >= p->n_mel) continue;
-      const int lead = p->mel_start[m] - slot_start[32 * i + l];
-      for (int j = 0; j < p->mel_cnt[m]; ++j)        // x 1/4: the conjugate split leaves the factor of the power out
-        melw[(size_t)(f.woff[i] + lead + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * 0.25f;
+  std::vector<float> melw;
+  // ---- interval form: slot s = the bins between the peaks of filters s and s + 1 (down-slope of s, up-slope of s + 1) ----
+  const int NBk = p->padded / 2;
+  auto W = [&](int m, int k) -> float {
+    return (m >= 0 && m < p->n_mel && k >= p->mel_start[m] && k < p->mel_start[m] + p->mel_cnt[m]) ? p->mel_w[p->mel_off[m] + k - p->mel_start[m]] : 0.f;
+  };
+  bool ival = !(getenv("B200FBANK_MEL_SLOTS") && strcmp(getenv("B200FBANK_MEL_SLOTS"), "filters") == 0);
+  std::vector<int> s_first(p->n_mel, -1), s_last(p->n_mel, -1), s_cnt(p->n_mel, 0);
+  for (int k = 0; k < NBk && ival; ++k) {
+    int lo = -1, hi = -1;
+    for (int m = 0; m < p->n_mel; ++m)
+      if (W(m, k) != 0.f) { if (lo < 0) lo = m; hi = m; }
+    if (lo < 0) continue;
+    int slot;
+    if (hi == lo + 1) slot = lo;
+    else if (hi == lo) {
+      int pk = p->mel_start[lo];
+      for (int j = 0; j < p->mel_cnt[lo]; ++j)
+        if (p->mel_w[p->mel_off[lo] + j] > W(lo, pk)) pk = p->mel_start[lo] + j;
+      slot = k <= pk ? lo - 1 : lo;                              // up-slope of filter lo (interval lo) or its down-slope
+    } else { ival = false; break; }
+    if (slot < 0) { ival = false; break; }                      // the first filter has an up-slope of its own: one slot per filter
+    if (s_first[slot] < 0) s_first[slot] = k;
+    if (s_last[slot] >= 0 && k != s_last[slot] + 1) { ival = false; break; }
+    s_last[slot] = k; ++s_cnt[slot];
+  }
+  if (ival) {
+    rows = 0;
+    for (int i = 0; i < f.groups; ++i) {
+      int mc = 1;
+      for (int sI = 32 * i; sI < std::min(32 * i + 32, p->n_mel); ++sI) mc = std::max(mc, s_cnt[sI]);
+      mc = (mc + 1) & ~1;                                        // even: the kernel's tap loop is unrolled by two
+      f.maxcnt[i] = mc; f.woff[i] = rows; rows += mc;
     }
+    f.rows = rows;
+    melw.assign((size_t)rows * 32 * 2, 0.f);                     // pairs (down-slope of filter s, up-slope of filter s + 1)
+    for (int i = 0; i < f.groups; ++i) {
+      // early starts inside each slot's slack so that the 16 lanes of a half-warp read 16 different 8-byte bank pairs
+      int sh[32] = {}, slack[32], cell[16];
+      for (int l = 0; l < 32; ++l) {
+        const int sI = 32 * i + l;
+        slack[l] = (sI < p->n_mel && s_cnt[sI] > 0) ? std::min(f.maxcnt[i] - s_cnt[sI], s_first[sI]) : 0;
+      }
+      auto cost = [&]() {
+        int c = 0;
+        for (int q = 0; q < 2; ++q) {
+          for (int l = 0; l < 16; ++l) {
+            const int sI = 32 * i + 16 * q + l;
+            cell[l] = (sI < p->n_mel && s_cnt[sI] > 0) ? s_first[sI] - sh[16 * q + l] : -1;
+          }
+          c += quarter_wavefronts(cell, 16);
+        }
+        return c;
+      };
+      uint64_t rng = 0x9E3779B97F4A7C15ull + (uint64_t)i;
+      auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+      int cur = cost(), best = cur, best_sh[32];
+      std::copy(sh, sh + 32, best_sh);
+      double T = 1.0;
+      for (int it = 0; it < 40000 && best > 2; ++it, T = std::max(0.05, T * 0.9998)) {
+        const int a = (int)(next() & 31);
+        if (slack[a] == 0) continue;
+        const int old = sh[a];
+        sh[a] = (int)(next() % (uint32_t)(slack[a] + 1));
+        const int c2 = cost();
+        const double u = (double)(next() & 0xFFFFFF) / (double)0x1000000;
+        if (c2 <= cur || u < std::exp((double)(cur - c2) / T)) {
+          cur = c2;
+          if (cur < best) { best = cur; std::copy(sh, sh + 32, best_sh); }
+        } else sh[a] = old;
+      }
+      for (int l = 0; l < 32; ++l) {
+        const int sI = 32 * i + l;
+        slot_bin[32 * i + l] = sI < p->n_mel ? sI : p->n_mel;
+        if (sI >= p->n_mel || s_cnt[sI] == 0) { slot_start[32 * i + l] = 0; continue; }
+        const int st = s_first[sI] - best_sh[l];
+        slot_start[32 * i + l] = st;
+        for (int j = 0; j < s_cnt[sI]; ++j) {                  // x 1/4: the conjugate split leaves the factor of the power out
+          const int k = s_first[sI] + j;
+          melw[((size_t)(f.woff[i] + best_sh[l] + j) * 32 + l) * 2] = W(sI, k) * 0.25f;
+          melw[((size_t)(f.woff[i] + best_sh[l] + j) * 32 + l) * 2 + 1] = W(sI + 1, k) * 0.25f;
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < f.groups; ++i) plan_mel_slots(p, i, f.maxcnt[i], slot_bin.data() + 32 * i, slot_start.data() + 32 * i, 16);
+    melw.assign((size_t)rows * 32, 0.f);
+    for (int i = 0; i < f.groups; ++i)
+      for (int l = 0; l < 32; ++l) {
+        const int m = slot_bin[32 * i + l];
+        if (m >= p->n_mel) continue;
+        const int lead = p->mel_start[m] - slot_start[32 * i + l];
+        for (int j = 0; j < p->mel_cnt[m]; ++j)        // x 1/4: the conjugate split leaves the factor of the power out
+          melw[(size_t)(f.woff[i] + lead + j) * 32 + l] = p->mel_w[p->mel_off[m] + j] * 0.25f;
+      }
+  }
+  f.interval = ival ? 1 : 0;
+  if (getenv("B200FBANK_VERBOSE"))
+    fprintf(stderr, "b200fbank: melspec fast kernel, %s slots, taps per group %d %d %d %d (%d rows)\n", ival ? "interval" : "filter",
+            f.maxcnt[0], f.maxcnt[1], f.maxcnt[2], f.maxcnt[3], f.rows);
   auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int {
     void* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
@@ -459,11 +590,14 @@ int setup_melfast(b200fbank_plan* p, std::vector<void*>& owned) {
     if (int rc = dev_copy(melw.data(), melw.size() * 4, (const void**)&f.melw)) return rc;
     if (int rc = dev_copy(slot_bin.data(), slot_bin.size() * 4, (const void**)&f.slot_bin)) return rc;
     if (int rc = dev_copy(slot_start.data(), slot_start.size() * 4, (const void**)&f.slot_start)) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<13, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<13, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<13, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<32, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    CUDA_TRY(cudaFuncSetAttribute(b200::melspec_fast_kernel<32, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   }
-  p->mfast_smem = (size_t)(2 * MS_N + ((rows * 32 + 3) & ~3) + MS_WARPS * (MS_EBUF + MS_TBUF)) * 4;
+  p->mfast_smem = (size_t)(2 * MS_N + (((ival ? 2 : 1) * rows * 32 + 3) & ~3) + MS_WARPS * (MS_EBUF + MS_TBUF)) * 4;
   if (p->mfast_smem > (size_t)kMaxSmemOptin) return 0;
+  if (p->device >= 0 && !p->counters.base && p->counters.init() != 0) return fail(B200FBANK_ERR_CUDA, "work-counter ring: allocation failed");
   p->melfast = (p->size <= 13 * 32 && p->shift == 5 * 32) ? 1 : 2;
   return 0;
 }
@@ -696,6 +830,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;
     if (const char* e = getenv("B200FBANK_PERSIST")) p->env_persist = atoi(e);
+    if (!p->counters.base && p->counters.init() != 0) return fail(B200FBANK_ERR_CUDA, "work-counter ring: allocation failed");
     f.ws_multi = 0;
     for (int i = 0; i < B200_MAX_RATES; ++i) f.ws_multi |= (f.ws_mode[i] >= 2);
 #define B200_WS_ATTR(S, A, M) CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<S, A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin))
@@ -806,20 +941,18 @@ int ws_pick_grid(const b200fbank_plan* p, const int64_t* d_offsets, b200::FastPa
   f.ws_persist = (mode != 0 && grid > sms) ? mode : 0;
   f.ws_counter = nullptr;
   if (f.ws_persist) grid = sms;
+  f.ws_counter_slot = -1;
   if (f.ws_persist == 2) {
-    // one work counter PER LAUNCH from the stream-ordered pool: it is released (ws_release_counter) behind the kernel
-    // on the same stream, so launches in flight on any number of streams never share one
-    void* d = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d, sizeof(int), st));
-    f.ws_counter = (int*)d;
-    CUDA_TRY(cudaMemsetAsync(f.ws_counter, 0, sizeof(int), st));
+    // one work counter PER LAUNCH in flight (CounterRing): released behind the kernel by ws_release_counter
+    f.ws_counter_slot = p->counters.acquire(st, &f.ws_counter);
+    if (f.ws_counter_slot < 0) return fail(B200FBANK_ERR_CUDA, "work counter: cudaMemsetAsync failed");
   }
   return 0;
 }
 
-int ws_release_counter(b200::FastParams& f, cudaStream_t st) {
-  if (f.ws_counter) CUDA_TRY(cudaFreeAsync(f.ws_counter, st));
-  f.ws_counter = nullptr;
+int ws_release_counter(const b200fbank_plan* p, b200::FastParams& f, cudaStream_t st) {
+  p->counters.release(f.ws_counter_slot, st);
+  f.ws_counter_slot = -1;
   return 0;
 }
 
@@ -951,7 +1084,7 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
       if (f.ast_bank) b200::fbank_ws_kernel<false, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
       else b200::fbank_ws_kernel<false, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
     }
-    if (int rc = ws_release_counter(f, st)) return rc;
+    if (int rc = ws_release_counter(p, f, st)) return rc;
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames);
@@ -1010,10 +1143,8 @@ int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int6
     b200::MelFastParams f = p->mfast;
     f.tiles_per_clip = (out_frames + b200::MS_TILE - 1) / b200::MS_TILE;
     if ((int64_t)B * f.tiles_per_clip > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * tiles exceeds 2^31 - 1");
-    void* d = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d, sizeof(int), st));
-    f.counter = (int*)d;
-    CUDA_TRY(cudaMemsetAsync(f.counter, 0, sizeof(int), st));
+    const int cslot = p->counters.acquire(st, &f.counter);
+    if (cslot < 0) return fail(B200FBANK_ERR_CUDA, "work counter: cudaMemsetAsync failed");
     static int sms = 0;
     if (sms == 0) {
       int n = 0;
@@ -1022,11 +1153,16 @@ int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int6
     }
     const int64_t warps_needed = (int64_t)B * f.tiles_per_clip;
     const int grid = (int)std::min<int64_t>(sms, (warps_needed + b200::MS_WARPS - 1) / b200::MS_WARPS);
-    if (p->melfast == 1) b200::melspec_fast_kernel<13, 5><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
-    else b200::melspec_fast_kernel<32, 0><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+    if (p->melfast == 1) {
+      if (f.interval) b200::melspec_fast_kernel<13, 5, true><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+      else b200::melspec_fast_kernel<13, 5, false><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+    } else {
+      if (f.interval) b200::melspec_fast_kernel<32, 0, true><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+      else b200::melspec_fast_kernel<32, 0, false><<<grid, b200::MS_THREADS, p->mfast_smem, st>>>(k, f);
+    }
     ++g_launches;
+    p->counters.release(cslot, st);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(d, st));
   } else {
     k.tiles = (out_frames + k.tile_frames - 1) / k.tile_frames;
     const int64_t grid = (int64_t)B * k.tiles;
@@ -1120,7 +1256,7 @@ int b200fbank_stats_accumulate(const b200fbank_plan* p, const float* d_wav, cons
       if (f.ast_bank) b200::fbank_ws_kernel<true, true, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
       else b200::fbank_ws_kernel<true, false, false><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, (cudaStream_t)stream>>>(k, f);
     }
-    if (int rc = ws_release_counter(f, (cudaStream_t)stream)) return rc;
+    if (int rc = ws_release_counter(p, f, (cudaStream_t)stream)) return rc;
   } else if (p->fast_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, max_frames);

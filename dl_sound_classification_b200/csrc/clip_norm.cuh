@@ -42,8 +42,62 @@ __device__ __forceinline__ void cn_block_sum(double& s, double& ss, double (*red
   }
 }
 
-// The clip's real cells as `rows` runs of `len` floats, `stride` floats apart: BTF = one run of m * n_cols, BFT = n_cols
-// runs of m.  VEC: every run starts 16-B aligned and len % 4 == 0 is not required (the tail is scalar).
+// The clip's real cells as R rows of Lr floats, S floats apart: BTF = m rows of n_cols, BFT = n_cols rows of m.  One
+// warp per row (rows strided over the CTA's warps), lanes along the row: scalar cells up to the first 16-B aligned
+// address of the row, float4 body, scalar tail -- no index division anywhere, coalesced whatever the row stride.
+template <class F>
+__device__ __forceinline__ void cn_for_rows(float* o, int R, int Lr, int S, F&& f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float* row = o + (size_t)r * S;
+    int head = (int)((4 - (((uintptr_t)row >> 2) & 3)) & 3);
+    head = head < Lr ? head : Lr;
+    if (lane < head) f.scalar(row + lane, r, lane);
+    const int nv = (Lr - head) >> 2;
+    float4* row4 = reinterpret_cast<float4*>(row + head);
+    for (int v = lane; v < nv; v += 32) f.vec(row4 + v, r, head + 4 * v);
+    const int t0 = head + 4 * nv;
+    if (lane < Lr - t0) f.scalar(row + t0 + lane, r, t0 + lane);
+  }
+}
+
+struct CnSum {
+  float floor_db; bool clamp; double s, ss;
+  __device__ __forceinline__ void scalar(float* q, int, int) {
+    float x = *q;
+    if (clamp) { x = fmaxf(x, floor_db); *q = x; }
+    s += (double)x; ss += (double)x * (double)x;
+  }
+  __device__ __forceinline__ void vec(float4* q, int, int) {
+    float4 x = *q;
+    if (clamp) {
+      x.x = fmaxf(x.x, floor_db); x.y = fmaxf(x.y, floor_db); x.z = fmaxf(x.z, floor_db); x.w = fmaxf(x.w, floor_db);
+      *q = x;
+    }
+    s += (double)((x.x + x.y) + (x.z + x.w));
+    ss += (double)(fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w));
+  }
+};
+
+struct CnApply {
+  float mu, sd, ts, tm; bool do_norm, do_mask; int layout, mk0, mk1, mk2, mk3;
+  // the reference's own three roundings: (x - mean) / std, * target_std, + target_mean; (r, e) = (row, position in the row)
+  __device__ __forceinline__ float cell(float x, int r, int e) const {
+    if (do_norm) x = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, mu), sd), ts), tm);
+    if (do_mask) {
+      const int t = layout == 0 ? r : e, col = layout == 0 ? e : r;
+      if ((t >= mk0 && t < mk0 + mk1) || (col >= mk2 && col < mk2 + mk3)) x = 0.f;
+    }
+    return x;
+  }
+  __device__ __forceinline__ void scalar(float* q, int r, int e) { *q = cell(*q, r, e); }
+  __device__ __forceinline__ void vec(float4* q, int r, int e) {
+    float4 x = *q;
+    x.x = cell(x.x, r, e); x.y = cell(x.y, r, e + 1); x.z = cell(x.z, r, e + 2); x.w = cell(x.w, r, e + 3);
+    __stcs(q, x);
+  }
+};
+
 __global__ void __launch_bounds__(CN_THREADS) clip_normalize_kernel(const ClipNormParams p) {
   __shared__ double red[2][32];
   __shared__ float s_mu, s_sd;
@@ -51,76 +105,30 @@ __global__ void __launch_bounds__(CN_THREADS) clip_normalize_kernel(const ClipNo
   int m = p.n_frames[b];
   m = m < 0 ? 0 : (m > p.out_frames ? p.out_frames : m);
   float* o = p.x + (size_t)b * p.out_frames * p.n_cols;
-  const int rows = p.layout == 0 ? 1 : p.n_cols;
-  const int len = p.layout == 0 ? m * p.n_cols : m;
-  const int stride = p.layout == 0 ? 0 : p.out_frames;
-  const bool vec = ((uintptr_t)o & 15) == 0 && (stride & 3) == 0;
-  const int nv = vec ? (len >> 2) : 0;                       // float4 per run
-  const int tail0 = nv << 2;                                 // scalar cells [tail0, len) of each run
+  const int R = p.layout == 0 ? m : p.n_cols, Lr = p.layout == 0 ? p.n_cols : m, S = p.layout == 0 ? p.n_cols : p.out_frames;
   const bool clamp = p.top_db >= 0.f && p.clip_max != nullptr;
-  const float floor_db = clamp ? p.clip_max[b] - p.top_db : -INFINITY;
-  double s = 0.0, ss = 0.0;
-  if (p.normalize || clamp) {
-    for (int w = tid; w < rows * nv; w += CN_THREADS) {
-      const int r = w / nv, v = w - r * nv;
-      float4* q = reinterpret_cast<float4*>(o + (size_t)r * stride) + v;
-      float4 x = *q;
-      if (clamp) {
-        x.x = fmaxf(x.x, floor_db); x.y = fmaxf(x.y, floor_db); x.z = fmaxf(x.z, floor_db); x.w = fmaxf(x.w, floor_db);
-        *q = x;
-      }
-      s += (double)((x.x + x.y) + (x.z + x.w));
-      ss += (double)(fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w));
-    }
-    const int nt = len - tail0;
-    for (int w = tid; w < rows * nt; w += CN_THREADS) {
-      const int r = w / nt, e = tail0 + (w - r * nt);
-      float* q = o + (size_t)r * stride + e;
-      float x = *q;
-      if (clamp) { x = fmaxf(x, floor_db); *q = x; }
-      s += (double)x; ss += (double)x * (double)x;
-    }
-  }
+  CnSum acc{clamp ? p.clip_max[b] - p.top_db : -INFINITY, clamp, 0.0, 0.0};
+  if (p.normalize || clamp) cn_for_rows(o, R, Lr, S, acc);
+  double s = acc.s, ss = acc.ss;
   cn_block_sum(s, ss, red);
   if (tid == 0) {
-    const double n = (double)rows * (double)len;
+    const double n = (double)R * (double)Lr;
     const double mu = n > 0 ? s / n : 0.0;
     const double var = n > 1 ? (ss - n * mu * mu) / (n - 1.0) : 0.0;      // torch .std(): unbiased
     s_mu = (float)mu;
     s_sd = (p.normalize && var > 0.0) ? (float)sqrt(var) : 0.f;
   }
   __syncthreads();
-  int mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+  CnApply ap;
+  ap.mk0 = ap.mk1 = ap.mk2 = ap.mk3 = 0;
   if (p.masks) {
-    mk0 = __ldg(p.masks + (size_t)b * 4 + 0); mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
-    mk2 = __ldg(p.masks + (size_t)b * 4 + 2); mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
+    ap.mk0 = __ldg(p.masks + (size_t)b * 4 + 0); ap.mk1 = __ldg(p.masks + (size_t)b * 4 + 1);
+    ap.mk2 = __ldg(p.masks + (size_t)b * 4 + 2); ap.mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
   }
-  const bool do_norm = s_sd > 0.f, do_mask = mk1 > 0 || mk3 > 0;
-  if (!do_norm && !do_mask) return;
-  const float mu = s_mu, sd = s_sd, ts = p.target_std, tm = p.target_mean;
-  // the reference's own three roundings: (x - mean) / std, * target_std, + target_mean
-  auto cell = [&](float x, int e, int r) -> float {
-    if (do_norm) x = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, mu), sd), ts), tm);
-    if (do_mask) {
-      const int t = p.layout == 0 ? e / p.n_cols : e;
-      const int col = p.layout == 0 ? e - t * p.n_cols : r;
-      if ((t >= mk0 && t < mk0 + mk1) || (col >= mk2 && col < mk2 + mk3)) x = 0.f;
-    }
-    return x;
-  };
-  for (int w = tid; w < rows * nv; w += CN_THREADS) {
-    const int r = w / nv, v = w - r * nv;
-    float4* q = reinterpret_cast<float4*>(o + (size_t)r * stride) + v;
-    float4 x = *q;
-    x.x = cell(x.x, 4 * v, r); x.y = cell(x.y, 4 * v + 1, r); x.z = cell(x.z, 4 * v + 2, r); x.w = cell(x.w, 4 * v + 3, r);
-    __stcs(q, x);
-  }
-  const int nt = len - tail0;
-  for (int w = tid; w < rows * nt; w += CN_THREADS) {
-    const int r = w / nt, e = tail0 + (w - r * nt);
-    float* q = o + (size_t)r * stride + e;
-    *q = cell(*q, e, r);
-  }
+  ap.do_norm = s_sd > 0.f; ap.do_mask = ap.mk1 > 0 || ap.mk3 > 0;
+  if (!ap.do_norm && !ap.do_mask) return;
+  ap.mu = s_mu; ap.sd = s_sd; ap.ts = p.target_std; ap.tm = p.target_mean; ap.layout = p.layout;
+  cn_for_rows(o, R, Lr, S, ap);
   // a mask may reach into the pad rows (t >= m): they are 0.0 already, nothing to do
 }
 

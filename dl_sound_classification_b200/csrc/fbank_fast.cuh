@@ -76,6 +76,7 @@ struct FastParams {
   int ws_persist;         // per launch: 0 = one item per CTA; 1 = grid of #SMs CTAs striding over the items (dense batches);
                           // 2 = the same with items claimed from ws_counter (ragged batches: uneven clips)
   int* ws_counter;        // per launch: zeroed device counter of the dynamic form
+  int ws_counter_slot;    // host side: its slot in the plan's counter ring (-1: none)
   const float* ws_t48;
   const float* ws_t22;
   const int* ws_k22;

@@ -15,7 +15,12 @@
 //   exchange  W_1024^(lane k1) twiddles, 32 x 33 padded transpose through the warp's shared-memory buffer
 //   stage 2   32-point DFT over n2 in registers (lane = k1), conjugate split of the two real spectra by shuffle, |.|^2
 //             for the 513 bins as (frame a, frame b) pairs
-//   mel       lane slots = mel bins (host-planned, LDS.64 per tap), 10 log10 through lg2.approx, running maximum
+//   mel       lane slots = the INTERVALS between neighbouring filter peaks: every FFT bin lies under exactly two triangles
+//             (the down-slope of filter s and the up-slope of filter s + 1), so the slot of interval s + 1 reads each of its
+//             bins ONCE (LDS.64 = both frames) and accumulates both slopes; filter s = its own down-slope sum + the
+//             up-slope sum of the previous slot (one shuffle).  Half the shared-memory reads of a slot per filter.
+//             (Banks whose first filter has an up-slope of its own keep one slot per filter.)  10 log10 through
+//             lg2.approx, running maximum
 //   store     (B, 1, n_mels, T): the tile's 8 x n_mels values are transposed through shared memory so that every row
 //             segment of 8 frames leaves as contiguous 8-byte stores; (B, T, n_mels): straight from the registers.
 #pragma once
@@ -31,15 +36,20 @@ constexpr int MS_N = 1024;
 constexpr int MS_EROW = 33;                          // float2 per exchange row (32 + 1 pad)
 constexpr int MS_EBUF = 32 * MS_EROW * 2;            // floats per warp: 32 x 33 complex; later 513 power pairs
 constexpr int MS_TILE = 8;                           // frames per tile
-constexpr int MS_TROW = 10;                          // floats per tile row: 8 frames + 2 pad (half-warp STS.64 conflict free)
+#ifndef B200_MS_TROW
+#define B200_MS_TROW 10
+#endif
+constexpr int MS_TROW = B200_MS_TROW;                // floats per tile row: 8 frames + 2 pad (half-warp STS.64 conflict free)
 constexpr int MS_TBUF = 128 * MS_TROW;               // floats per warp
 constexpr float MS_DB_PER_LG2 = 3.0102999566398120f; // 10 log10(2)
 
 struct MelFastParams {
   const float2* tw;        // [32][32] W_1024^(k1 * lane)
-  const float* melw;       // [rows][32] zero-padded weights (x 1/4: the conjugate split leaves the factor out), lanes = slots
+  const float* melw;       // [rows][32] zero-padded weights (x 1/4: the conjugate split leaves the factor out), lanes = slots;
+                           // interval form: [rows][32] PAIRS (down-slope weight of filter s, up-slope weight of filter s + 1)
   const int* slot_bin;     // [32 groups'] mel bin of lane slot (group i, lane l), >= n_mel: none
   const int* slot_start;   // first FFT bin the slot reads
+  int interval;            // 1: slots are intervals (natural order, slot s = filter s), 0: one slot per filter
   int groups, maxcnt[4], woff[4], rows;
   int tiles_per_clip;
   int* counter;            // per launch: zeroed tile counter
@@ -112,31 +122,49 @@ __device__ __forceinline__ void ms_pair_power(const float (&xa)[NJ], const float
   __syncwarp();
 }
 
-template <int NJ, int SJ>       // SJ > 0: hop == 32 SJ, frame b's sample j is frame a's sample j + SJ (shared loads)
+// Reflect padding of torch.stft (a function of the absolute index) + a clamp for the cells under the zero part of the window.
+__device__ __forceinline__ float ms_ld_edge(const float* __restrict__ x, int64_t v, int64_t n) {
+  v = reflect_index(v, n, 2);
+  v = v < 0 ? 0 : (v >= n ? n - 1 : v);
+  return __ldg(x + v);
+}
+
+// NJ / SJ: see above (SJ > 0: hop == 32 SJ, frame b's sample j is frame a's sample j + SJ: shared loads).
+// IVAL: mel slots are intervals (melw2 = (down-slope of filter s, up-slope of filter s + 1) pairs), else one slot per filter.
+template <int NJ, int SJ, bool IVAL>
 __global__ void __launch_bounds__(MS_THREADS, 1) melspec_fast_kernel(const FbankParams p, const MelFastParams mp) {
   extern __shared__ __align__(16) float smem[];
   float2* stw = reinterpret_cast<float2*>(smem);                 // [1024]
-  float* smelw = smem + 2 * MS_N;                                // [rows * 32]
-  float* ebuf = smelw + ((mp.rows * 32 + 3) & ~3);               // [MS_WARPS][MS_EBUF]
+  float* smelw = smem + 2 * MS_N;                                // IVAL: [rows][32] float2 (down, up); else [rows][32] float
+  constexpr int WPS = IVAL ? 2 : 1;                              // floats per weight slot
+  float* ebuf = smelw + ((WPS * mp.rows * 32 + 3) & ~3);         // [MS_WARPS][MS_EBUF]
   float* tbuf = ebuf + MS_WARPS * MS_EBUF;                       // [MS_WARPS][MS_TBUF]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < MS_N; i += MS_THREADS) stw[i] = __ldg(mp.tw + i);
-  for (int i = tid; i < mp.rows * 32; i += MS_THREADS) smelw[i] = __ldg(mp.melw + i);
+  for (int i = tid; i < WPS * mp.rows * 32; i += MS_THREADS) smelw[i] = __ldg(mp.melw + i);
   __syncthreads();
   float* Ebuf = ebuf + warp * MS_EBUF;
   float* Tb = tbuf + warp * MS_TBUF;
   float w[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) w[j] = (lane + 32 * j < p.size) ? __ldg(p.window + lane + 32 * j) : 0.f;
-  int mstart[4], mbin[4];
+  // per-lane constants of the mel / store stages: first power pair of the slot, its weight column, its tile row
+  const float2* mp2[4];
+  const float* mw[4];
+  float* trow[4];
+  int mbin[4], mcnt[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool have = i < mp.groups;
     mbin[i] = have ? __ldg(mp.slot_bin + lane + 32 * i) : p.n_mel;
-    mstart[i] = have ? __ldg(mp.slot_start + lane + 32 * i) : 0;
+    mp2[i] = reinterpret_cast<const float2*>(Ebuf) + (have ? __ldg(mp.slot_start + lane + 32 * i) : 0);
+    mw[i] = smelw + WPS * (mp.woff[i] * 32 + lane);
+    mcnt[i] = have ? mp.maxcnt[i] : 0;
+    trow[i] = Tb + (mbin[i] < p.n_mel ? mbin[i] : 0) * MS_TROW;
   }
   const int total = p.B * mp.tiles_per_clip;
   const int half = p.size >> 1;
+  const bool bft = p.layout != 0, db = p.db_mode != 0;
   int next = 0;
   if (lane == 0) next = atomicAdd(mp.counter, 1);
   for (;;) {
@@ -152,114 +180,157 @@ __global__ void __launch_bounds__(MS_THREADS, 1) melspec_fast_kernel(const Fbank
     const float* __restrict__ x = c.wav;
     const int64_t n = c.n_in;
     float vmax = -INFINITY;
+    // ---- stage 0: samples lane + 32 j of the frames (frame t starts at t * hop - size / 2).  With hop == 32 SJ the two frames
+    // of a pass share their loads (frame b's sample j is frame a's sample j + SJ) and so do consecutive passes: the window
+    // of NL = NJ + SJ registers slides by 2 SJ per pass, and the 2 SJ new samples are loaded one pass AHEAD.
+    constexpr int NL = SJ > 0 ? NJ + SJ : NJ;
+    constexpr int NS = 2 * SJ;                                   // registers the window slides by per pass
+    const int64_t base0 = (int64_t)t0 * p.shift - half;
+    // the whole tile (all four passes, look-ahead included) inside the clip: plain loads at constant offsets from one
+    // pointer; otherwise every index goes through the reflect padding
+    const bool interior = base0 >= 0 && base0 + 32 * (NL + 3 * (SJ > 0 ? NS : 0)) + (SJ > 0 ? 0 : 7 * p.shift) <= n;
+    const float* __restrict__ xp = x + base0 + lane;             // sample `lane` of the pass's first frame
+    float xl[NL];
+    if (SJ > 0 && t0 < m_eff) {
+      if (interior) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) xl[j] = __ldg(xp + 32 * j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) xl[j] = ms_ld_edge(x, base0 + lane + 32 * j, n);
+      }
+    }
 #pragma unroll 1
     for (int pi = 0; pi < MS_TILE / 2; ++pi) {
       const int ta = t0 + 2 * pi;
       if (ta >= t_end) break;
       const bool live_a = ta < m_eff, live_b = ta + 1 < m_eff;
-      float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 y[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (live_a) {
-        // ---- stage 0: samples lane + 32 j of the two frames (frame t starts at t * hop - size / 2) ----
-        const int64_t base = (int64_t)ta * p.shift - half;
-        constexpr int NL = SJ > 0 ? NJ + SJ : NJ;
-        float xl[NL], xa[NJ], xb[NJ];            // (the reflect padding is a function of the absolute index: shared loads stay valid at the edges)
-        const bool interior = base >= 0 && base + 32 * (SJ > 0 ? NL : NJ) + (SJ > 0 ? 0 : p.shift) <= n;
-        if (interior) {
+        float xa[NJ], xb[NJ];
+        if constexpr (SJ > 0) {
+          float xn[NS];
+          if (pi + 1 < MS_TILE / 2 && ta + 2 < m_eff) {          // the next pass's new samples, in flight during this pass
+            if (interior) {
 #pragma unroll
-          for (int j = 0; j < NL; ++j) xl[j] = __ldg(x + base + lane + 32 * j);
-          if constexpr (SJ == 0) {
+              for (int i = 0; i < NS; ++i) xn[i] = __ldg(xp + 32 * (NL + i));
+            } else {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) xb[j] = __ldg(x + base + p.shift + lane + 32 * j);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < NL; ++j) {
-            int64_t v = reflect_index(base + lane + 32 * j, n, 2);
-            v = v < 0 ? 0 : (v >= n ? n - 1 : v);               // only cells under the zero part of the window can land here
-            xl[j] = __ldg(x + v);
-          }
-          if constexpr (SJ == 0) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-              int64_t v = reflect_index(base + p.shift + lane + 32 * j, n, 2);
-              v = v < 0 ? 0 : (v >= n ? n - 1 : v);
-              xb[j] = __ldg(x + v);
+              for (int i = 0; i < NS; ++i) xn[i] = ms_ld_edge(x, base0 + (int64_t)(2 * pi) * p.shift + lane + 32 * (NL + i), n);
             }
           }
-        }
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          xa[j] = xl[j];
-          if constexpr (SJ > 0) xb[j] = xl[j + SJ];
+          for (int j = 0; j < NJ; ++j) { xa[j] = xl[j]; xb[j] = xl[j + SJ]; }
+#pragma unroll
+          for (int j = 0; j < NL - NS; ++j) xl[j] = xl[j + NS];
+#pragma unroll
+          for (int i = 0; i < NS; ++i) xl[NL - NS + i] = xn[i];
+        } else {
+          if (interior) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { xa[j] = __ldg(xp + 32 * j); xb[j] = __ldg(xp + p.shift + 32 * j); }
+          } else {
+            const int64_t base = base0 + (int64_t)(2 * pi) * p.shift;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { xa[j] = ms_ld_edge(x, base + lane + 32 * j, n); xb[j] = ms_ld_edge(x, base + p.shift + lane + 32 * j, n); }
+          }
         }
+        xp += 2 * p.shift;
         if (!live_b) {
 #pragma unroll
           for (int j = 0; j < NJ; ++j) xb[j] = 0.f;
         }
         ms_pair_power<NJ>(xa, xb, w, stw, Ebuf, lane);
-        // ---- mel (lane slots = bins), dB ----
-        const float2* P2 = reinterpret_cast<const float2*>(Ebuf);
+        // ---- mel (lane slots), dB ----
+        fk_u64 prev_up = 0ull;                                  // interval form: up-slope sum of lane 31's slot in the previous group
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (i >= mp.groups) continue;
-          const float* wrow = smelw + mp.woff[i] * 32 + lane;
-          const float2* pp = P2 + mstart[i];
+          const float2* pp = mp2[i];
           fk_u64 acc = 0ull;
-          const int cnt = mp.maxcnt[i];
-#pragma unroll 4
-          for (int j = 0; j < cnt; ++j) {
-            const float wj = wrow[j * 32];
-            const float2 pv = pp[j];
-            acc = fk_fma2(fk_pk(wj, wj), fk_pk(pv.x, pv.y), acc);
+          if constexpr (IVAL) {
+            const float2* wr = reinterpret_cast<const float2*>(mw[i]);
+            fk_u64 up = 0ull;
+#pragma unroll 2
+            for (int j = 0; j < mcnt[i]; ++j) {                  // (host: counts padded to even)
+              const float2 wd = wr[j * 32];
+              const float2 pv = pp[j];
+              const fk_u64 p2 = fk_pk(pv.x, pv.y);
+              acc = fk_fma2(fk_pk(wd.x, wd.x), p2, acc);
+              up = fk_fma2(fk_pk(wd.y, wd.y), p2, up);
+            }
+            // filter s = down-slope sum of slot s + up-slope sum of slot s - 1 (lane 0: lane 31 of the previous group)
+            const fk_u64 recv = __shfl_sync(0xffffffffu, lane == 31 ? prev_up : up, (lane + 31) & 31);
+            acc = fk_add2(acc, recv);
+            prev_up = __shfl_sync(0xffffffffu, up, 31);
+          } else {
+            const float* wr = mw[i];
+#pragma unroll 2
+            for (int j = 0; j < mcnt[i]; ++j) {
+              const float wj = wr[j * 32];
+              const float2 pv = pp[j];
+              acc = fk_fma2(fk_pk(wj, wj), fk_pk(pv.x, pv.y), acc);
+            }
           }
-          const float2 a = fk_upk(acc);
-          float va = a.x, vb = a.y;
-          if (p.db_mode) {                                      // 10 log10(max(x, 1e-10)), functional.py:390-396 (ref = 1, power)
+          float2 v = fk_upk(acc);
+          if (db) {                                             // 10 log10(max(x, 1e-10)), functional.py:390-396 (ref = 1, power)
             float la, lb;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"(fmaxf(va, 1e-10f)));
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lb) : "f"(fmaxf(vb, 1e-10f)));
-            va = la * MS_DB_PER_LG2; vb = lb * MS_DB_PER_LG2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"(fmaxf(v.x, 1e-10f)));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lb) : "f"(fmaxf(v.y, 1e-10f)));
+            v.x = la * MS_DB_PER_LG2; v.y = lb * MS_DB_PER_LG2;
           }
-          ya[i] = va;
-          yb[i] = live_b ? vb : 0.f;
-          if (mbin[i] < p.n_mel) vmax = fmaxf(vmax, live_b ? fmaxf(va, vb) : va);
+          if (!live_b) v.y = v.x;                               // (keeps the pad frame out of the maximum; stored as 0 below)
+          if (mbin[i] < p.n_mel) vmax = fmaxf(vmax, fmaxf(v.x, v.y));
+          if (!live_b) v.y = 0.f;
+          y[i] = v;
         }
+      } else {
+        xp += 2 * p.shift;
       }
       // ---- hand the pair to the store stage ----
-      if (p.layout == 0) {
+      if (!bft) {
         float* o = p.out + ((size_t)b * p.out_frames + ta) * p.n_cols;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (i < mp.groups && mbin[i] < p.n_mel) {
-            o[mbin[i]] = ya[i];
-            if (ta + 1 < t_end) o[p.n_cols + mbin[i]] = yb[i];
+          if (mbin[i] < p.n_mel) {
+            o[mbin[i]] = y[i].x;
+            if (ta + 1 < t_end) o[p.n_cols + mbin[i]] = y[i].y;
           }
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (i < mp.groups && mbin[i] < p.n_mel)
-            *reinterpret_cast<float2*>(Tb + mbin[i] * MS_TROW + 2 * pi) = make_float2(ya[i], yb[i]);
+          if (mbin[i] < p.n_mel) *reinterpret_cast<float2*>(trow[i] + 2 * pi) = y[i];
       }
     }
-    if (p.layout != 0) {
-      // ---- (B, 1, n_mels, T): row segments of the tile, 8 rows x 4 column pairs per instruction ----
+    if (bft) {
+      // ---- (B, 1, n_mels, T): row segments of the tile, 8 rows x 4 column pairs per instruction.  A lane's 8-byte alignment
+      // is the same for all its rows (8 rows further = 32 T bytes), so the aligned / scalar choice is made once. ----
       __syncwarp();
       const int cpair = lane & 3;
       const int t = t0 + 2 * cpair;
-      float* ob = p.out + (size_t)b * p.n_cols * p.out_frames + t;
-      for (int r0 = 0; r0 < p.n_mel; r0 += 8) {
-        const int r = r0 + (lane >> 2);
-        if (r < p.n_mel && t < t_end) {
-          const float2 v = *reinterpret_cast<const float2*>(Tb + r * MS_TROW + 2 * cpair);
-          float* q = ob + (size_t)r * p.out_frames;
-          if (t + 1 < t_end && (((uintptr_t)q) & 7) == 0) *reinterpret_cast<float2*>(q) = v;
-          else { q[0] = v.x; if (t + 1 < t_end) q[1] = v.y; }
+      if (t < t_end) {
+        const bool two = t + 1 < t_end;
+        float* q = p.out + ((size_t)b * p.n_cols + (lane >> 2)) * p.out_frames + t;
+        const float* tr = Tb + (lane >> 2) * MS_TROW + 2 * cpair;
+        const size_t qstep = (size_t)8 * p.out_frames;
+        const bool al = two && ((uintptr_t)q & 7) == 0;
+        const int nr = (p.n_mel - (lane >> 2) + 7) >> 3;        // rows of this lane
+        if (al) {
+#pragma unroll 4
+          for (int r = 0; r < nr; ++r) { *reinterpret_cast<float2*>(q) = *reinterpret_cast<const float2*>(tr); q += qstep; tr += 8 * MS_TROW; }
+        } else {
+#pragma unroll 4
+          for (int r = 0; r < nr; ++r) {
+            const float2 v = *reinterpret_cast<const float2*>(tr);
+            q[0] = v.x;
+            if (two) q[1] = v.y;
+            q += qstep; tr += 8 * MS_TROW;
+          }
         }
       }
       __syncwarp();
     }
-    if (p.db_mode && p.clip_max) {
+    if (db && p.clip_max) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
       if (lane == 0 && vmax > -INFINITY) atomic_max_float(p.clip_max + b, vmax);
