@@ -181,7 +181,7 @@ __device__ __forceinline__ int fk_load_x_async(const float* g /* = clip + in_lo 
   return sh;
 }
 
-// Per-lane constants of the frame pass (live for the whole kernel).
+// Per-lane constants of the frame pass (live for the whole kernel).   // [phase: -] (helpers: charged to their caller)
 struct FkLane {
   float win[13];        // window at n = lane + 32 j
   int mstart[4];        // first FFT bin read by lane slot (i, lane)

@@ -68,14 +68,14 @@ __host__ __device__ constexpr int ws_off(int r) { return r == 0 ? 0 : r == 1 ? 2
 __host__ __device__ constexpr int ws_off1(int r) { return r == 0 ? 0 : r == 1 ? 2 : r == 2 ? 4 : r == 3 ? 8 : 10; }
 __host__ __device__ constexpr int ws_offc(int cls, int r) { return cls ? ws_off1(r) : ws_off(r); }
 
-// ---- mbarrier / named barrier / register reallocation --------------------------------------------
+// ---- mbarrier / named barrier / register reallocation --------------------------------------------   // [phase: -]
 __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, unsigned parity) {   // [phase: mbar_wait]
   const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile(
       "{\n"
@@ -87,6 +87,7 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, unsigned parity) {
       "WS_DONE_%=:\n"
       "}\n" ::"r"(a), "r"(parity), "r"(WS_WAIT_HINT_NS) : "memory");
 }
+// [phase: -]
 __device__ __forceinline__ void ws_bar_r() { asm volatile("bar.sync 1, %0;" ::"n"(WS_R_THREADS) : "memory"); }
 
 // 1-D bulk copy global -> shared through the TMA unit (UBLKCP): one instruction moves the whole input chunk and
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
       sq[8] = 1;
       pend = ws_claim(fp, total);
     }
-    for (int k = 0;; ++k) {
+    for (int k = 0;; ++k) {                                      // [phase: ws_item_ctl]
       int item;
       if (dyn) {
         if (rt == 0) {                                           // publish item k + 1, start claiming item k + 2
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           k0 = __ldg(fp.ws_k22 + par * 32 + g);
         }
       }
-      // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy
+      // stage the input of a chunk: x[in_lo, in_lo + nx) -> xbuf[sh + i]; interior chunks take ONE TMA bulk copy   // [phase: ws_stage_x]
       auto stage_x = [&](int64_t in_lo, int nx) -> int {
         const float* gsrc = c.wav + in_lo;
         const int sh = ws_shift(gsrc);
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc - sh), "r"((unsigned)(((nx + sh + 3) >> 2) << 4)) : "memory");
         }
       };
-      auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {
+      auto put_hop = [&](float* rb, int slot, int q, const float (&y)[FK_RP]) {   // [phase: ws_put_hop]
         float* o = rb + q * FK_SHIFT + FK_RP * g;
 #pragma unroll
         for (int r = 0; r < FK_RP; ++r) o[r] = y[r];
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           for (int r = 0; r < FK_RP; ++r) om[r] = y[r];
         }
       };
+      // [phase: ws_chunk_ctl]
       // one loop per mode (not one loop with the mode switch inside): only the state of the running mode stays live in
       // registers, which is what lets ptxas issue the input loads of a hop well ahead of the FFMA2 chain
       auto run_chunks = [&](auto&& chunk_body) {
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           const long long tb_ = clock64();
           WS_TACC(0, ta_);
 #endif
-          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
+          if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));   // [phase: ws_resample_441]
 #ifdef B200_WS_TIMING
           tc_ = clock64();
           WS_TACC(1, tb_);

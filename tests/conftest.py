@@ -22,3 +22,14 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name))
     return load
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Table of every log-mel comparison of the run: max-abs on well-conditioned cells, on the near-floor carve-out, and
+    the carve-out's population (tests/parity.py)."""
+    import parity
+    if not parity.REPORT:
+        return
+    terminalreporter.write_line("log-mel parity (max-abs main | near-floor | carve-out cells / cells):")
+    for what, main, floor, n_floor, cells in parity.REPORT:
+        terminalreporter.write_line(f"  {what[:70]:70s} {main:.2e} | {floor:.2e} | {n_floor} / {cells}")
