@@ -510,7 +510,21 @@ def run_extras(args, torch, dist, b2, dev, rank, world, barrier):
     ms = timed(lambda: fe(wav[:1024], OUT_FRAMES, out=o1, per_clip_norm=True, return_n_frames=False), 20)
     out["per_clip_norm"] = dict(workload="1024 ESC-50 clips per GPU, kaldi recipe + per-clip mean / unbiased-std normalisation (2 kernels)",
                                 ms_per_step=ms, value=world * 1024 * CLIP_SECONDS / (ms * 1e-3), unit=UNIT)
-    del wav, out_b
+    # ---- Mixup fused into the epilogue vs frontend + stand-alone mixup kernel (every clip mixed, 2048-clip bank) ----
+    NB = 2048
+    bank = torch.randn((NB, OUT_FRAMES, N_MELS), generator=gen, device=dev)
+    gm = torch.Generator().manual_seed(5 + rank)
+    plan = b2.MixupPlan(torch.randint(0, NB, (1024,), generator=gm).int(), torch.rand(1024, generator=gm)).to(dev)
+
+    def two_launches():
+        fe(wav[:1024], OUT_FRAMES, mean=mean, std=std, out=o1, return_n_frames=False)
+        b2.mixup_batch(o1, bank, plan, out=o1)
+    ms2 = timed(two_launches, 20)
+    ms1 = timed(lambda: fe(wav[:1024], OUT_FRAMES, mean=mean, std=std, out=o1, return_n_frames=False, mixup=(bank, plan)), 20)
+    out["mixup_fused"] = dict(workload="1024 ESC-50 clips per GPU, every clip mixed with a partner from a 2048-clip bank in HBM: Mixup in the fbank "
+                                       "epilogue (b200fbank_execute_mixup) vs frontend + stand-alone mixup kernel",
+                              ms_per_step=ms1, ms_two_launches=ms2, value=world * 1024 * CLIP_SECONDS / (ms1 * 1e-3), unit=UNIT)
+    del wav, out_b, bank
     # ---- the reference-actual recipe ------------------------------------
     Bm = 256
     wm = torch.rand((Bm, CLIP_SAMPLES), generator=gen, device=dev) * 2 - 1

@@ -74,6 +74,9 @@ def _load():
     lib.b200fbank_execute.argtypes = [P, VP, VP, I64, VP, C.c_int, VP, VP, VP, C.c_int, F32, F32, C.c_int,
                                       C.c_int, VP, VP, VP]
     lib.b200fbank_execute.restype = C.c_int
+    lib.b200fbank_execute_mixup.argtypes = [P, VP, VP, I64, VP, C.c_int, VP, VP, VP, C.c_int, F32, F32, C.c_int,
+                                            C.c_int, VP, VP, VP, VP, VP, VP]
+    lib.b200fbank_execute_mixup.restype = C.c_int
     lib.b200fbank_melspec_db.argtypes = [P, VP, VP, I64, VP, C.c_int, VP, C.c_int, C.c_int, F32, F32, C.c_int, C.c_int,
                                          VP, VP, VP, VP]
     lib.b200fbank_melspec_db.restype = C.c_int
@@ -109,7 +112,7 @@ lib = _load()
 EXPORTED_SYMBOLS = [
     "b200fbank_abi_version", "b200fbank_sizeof_opts", "b200fbank_default_opts", "b200fbank_plan_create", "b200fbank_plan_destroy",
     "b200fbank_last_error", "b200fbank_mixup", "b200fbank_mixup_labels", "b200fbank_patch_embed", "b200fbank_resampled_length", "b200fbank_num_frames", "b200fbank_num_cols",
-    "b200fbank_plan_table", "b200fbank_plan_info", "b200fbank_execute", "b200fbank_melspec_db",
+    "b200fbank_plan_table", "b200fbank_plan_info", "b200fbank_execute", "b200fbank_execute_mixup", "b200fbank_melspec_db",
     "b200fbank_stats_accumulate", "b200fbank_clip_normalize", "b200fbank_remove_clip_mean", "b200fbank_pcm16_to_float",
     "b200fbank_resample", "b200fbank_launch_count",
 ]

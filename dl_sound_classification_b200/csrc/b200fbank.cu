@@ -184,7 +184,7 @@ struct b200fbank_plan {
   // device copies
   void* d_blob = nullptr;
   std::vector<void*> owned;           // further device allocations
-  b200::FbankParams base;             // table pointers + scalars filled once
+  b200::FbankParams base{};           // table pointers + scalars filled once
   int generic_threads = 256;
   size_t generic_smem = 0;
   // fast (AST-configuration) kernel
@@ -1046,11 +1046,12 @@ int b200fbank_plan_info(const b200fbank_plan* p, int arg, int64_t info[8]) {
   return 0;
 }
 
-int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
-                      int64_t clip_samples, const int32_t* d_rate_id, int B,
-                      const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
-                      float target_mean, float target_std, int out_frames, int layout,
-                      float* d_out, int32_t* d_n_frames, void* stream) {
+static int execute_impl(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                        int64_t clip_samples, const int32_t* d_rate_id, int B,
+                        const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                        float target_mean, float target_std, int out_frames, int layout,
+                        const float* d_bank, const int32_t* d_partner, const float* d_lam,
+                        float* d_out, int32_t* d_n_frames, void* stream) {
   int rc = check_device_call(p, d_wav, d_offsets, clip_samples, B);
   if (rc) return rc;
   if (out_frames <= 0) return fail(B200FBANK_ERR_INVALID, "out_frames must be > 0");
@@ -1070,6 +1071,11 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
   k.target_mean = target_mean; k.target_std = target_std;
   const bool cms = p->o.subtract_mean != 0;
   if (cms) { k.masks = nullptr; k.n_stats = 0; }     // raw features first, cms_kernel finishes
+  // Mixup rides in the epilogue of the tuned kernels; the generic kernel (and CMS, which finishes in a second kernel)
+  // mix with one more launch of the stand-alone mixup kernel, in place
+  const bool mix = d_bank != nullptr;
+  const bool mix_fused = mix && p->fast_ok && !cms;
+  if (mix_fused) { k.mix_bank = d_bank; k.mix_partner = d_partner; k.mix_lam = d_lam; }
   if (p->fast_ok && p->ws_ok) {
     b200::FastParams f = p->fast;
     f.seg_frames = pick_seg_frames(f, B, out_frames, 148);
@@ -1107,7 +1113,30 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
   }
+  if (mix && !mix_fused)
+    return b200fbank_mixup(d_out, d_bank, d_partner, d_lam, B, (int64_t)out_frames * p->n_cols, d_out, stream);
   return 0;
+}
+
+int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                      int64_t clip_samples, const int32_t* d_rate_id, int B,
+                      const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                      float target_mean, float target_std, int out_frames, int layout,
+                      float* d_out, int32_t* d_n_frames, void* stream) {
+  return execute_impl(p, d_wav, d_offsets, clip_samples, d_rate_id, B, d_masks, d_mean, d_std, n_stats, target_mean,
+                      target_std, out_frames, layout, nullptr, nullptr, nullptr, d_out, d_n_frames, stream);
+}
+
+int b200fbank_execute_mixup(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                            int64_t clip_samples, const int32_t* d_rate_id, int B,
+                            const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                            float target_mean, float target_std, int out_frames, int layout,
+                            const float* d_bank, const int32_t* d_partner, const float* d_lam,
+                            float* d_out, int32_t* d_n_frames, void* stream) {
+  if (!d_bank || !d_partner || !d_lam) return fail(B200FBANK_ERR_INVALID, "d_bank / d_partner / d_lam are NULL");
+  if (d_bank == d_out) return fail(B200FBANK_ERR_INVALID, "the bank must not alias the output");
+  return execute_impl(p, d_wav, d_offsets, clip_samples, d_rate_id, B, d_masks, d_mean, d_std, n_stats, target_mean,
+                      target_std, out_frames, layout, d_bank, d_partner, d_lam, d_out, d_n_frames, stream);
 }
 
 int b200fbank_melspec_db(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets, int64_t clip_samples,

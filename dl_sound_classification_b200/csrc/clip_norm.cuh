@@ -1,4 +1,5 @@
-// Per-clip passes around the fused frontend: one CTA per clip, the clip read twice (the second read comes from L2).
+// Per-clip passes around the fused frontend: one CTA per clip, the clip read twice (the second read comes from L2) and
+// written once (the top_db clamp is applied on the fly by both passes).
 //
 //   clip_normalize_kernel  AmplitudeToDB's top_db clamp (torchaudio/functional/functional.py:398-402) and the reference's
 //                          per-clip normalisation (ASTPreprocessor.preprocess, src/datasets/preprocessing.py:1027-1037):
@@ -65,24 +66,22 @@ struct CnSum {
   float floor_db; bool clamp; double s, ss;
   __device__ __forceinline__ void scalar(float* q, int, int) {
     float x = *q;
-    if (clamp) { x = fmaxf(x, floor_db); *q = x; }
+    if (clamp) x = fmaxf(x, floor_db);                    // (written by the second pass only: one store per cell)
     s += (double)x; ss += (double)x * (double)x;
   }
   __device__ __forceinline__ void vec(float4* q, int, int) {
     float4 x = *q;
-    if (clamp) {
-      x.x = fmaxf(x.x, floor_db); x.y = fmaxf(x.y, floor_db); x.z = fmaxf(x.z, floor_db); x.w = fmaxf(x.w, floor_db);
-      *q = x;
-    }
+    if (clamp) { x.x = fmaxf(x.x, floor_db); x.y = fmaxf(x.y, floor_db); x.z = fmaxf(x.z, floor_db); x.w = fmaxf(x.w, floor_db); }
     s += (double)((x.x + x.y) + (x.z + x.w));
     ss += (double)(fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w));
   }
 };
 
 struct CnApply {
-  float mu, sd, ts, tm; bool do_norm, do_mask; int layout, mk0, mk1, mk2, mk3;
+  float mu, sd, ts, tm, floor_db; bool do_norm, do_mask, clamp; int layout, mk0, mk1, mk2, mk3;
   // the reference's own three roundings: (x - mean) / std, * target_std, + target_mean; (r, e) = (row, position in the row)
   __device__ __forceinline__ float cell(float x, int r, int e) const {
+    if (clamp) x = fmaxf(x, floor_db);
     if (do_norm) x = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, mu), sd), ts), tm);
     if (do_mask) {
       const int t = layout == 0 ? r : e, col = layout == 0 ? e : r;
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(CN_THREADS) clip_normalize_kernel(const ClipNo
   const int R = p.layout == 0 ? m : p.n_cols, Lr = p.layout == 0 ? p.n_cols : m, S = p.layout == 0 ? p.n_cols : p.out_frames;
   const bool clamp = p.top_db >= 0.f && p.clip_max != nullptr;
   CnSum acc{clamp ? p.clip_max[b] - p.top_db : -INFINITY, clamp, 0.0, 0.0};
-  if (p.normalize || clamp) cn_for_rows(o, R, Lr, S, acc);
+  if (p.normalize) cn_for_rows(o, R, Lr, S, acc);        // statistics of the clamped values; clamp-only runs need no first pass
   double s = acc.s, ss = acc.ss;
   cn_block_sum(s, ss, red);
   if (tid == 0) {
@@ -126,7 +125,8 @@ __global__ void __launch_bounds__(CN_THREADS) clip_normalize_kernel(const ClipNo
     ap.mk2 = __ldg(p.masks + (size_t)b * 4 + 2); ap.mk3 = __ldg(p.masks + (size_t)b * 4 + 3);
   }
   ap.do_norm = s_sd > 0.f; ap.do_mask = ap.mk1 > 0 || ap.mk3 > 0;
-  if (!ap.do_norm && !ap.do_mask) return;
+  ap.clamp = clamp; ap.floor_db = acc.floor_db;
+  if (!ap.do_norm && !ap.do_mask && !clamp) return;
   ap.mu = s_mu; ap.sd = s_sd; ap.ts = p.target_std; ap.tm = p.target_mean; ap.layout = p.layout;
   cn_for_rows(o, R, Lr, S, ap);
   // a mask may reach into the pad rows (t >= m): they are 0.0 already, nothing to do

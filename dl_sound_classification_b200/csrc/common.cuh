@@ -52,6 +52,11 @@ struct FbankParams {
   float target_mean, target_std;
   float* out;
   int32_t* n_frames_out;
+  // Mixup fused into the epilogue (tuned kernels only): out = lam * y + (1 - lam) * bank[partner] cell by cell, with the
+  // reference's three roundings (csrc/mixup.cuh); the bank holds spectrograms in the SAME layout and out_frames as `out`
+  const float* mix_bank;     // (N, out_frames, n_cols) / (N, 1, n_cols, out_frames), or nullptr
+  const int32_t* mix_partner;   // [B] index into the bank, < 0: clip left alone
+  const float* mix_lam;      // [B]
   double* sums;              // stats mode: [2*n_cols+1]
   int max_frames;            // stats mode frame cap
   int tile_frames;           // F: frames per CTA

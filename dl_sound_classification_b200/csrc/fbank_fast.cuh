@@ -330,6 +330,22 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   constexpr int f0 = 0;
   const int nf = n_live;
   (void)mk2; (void)mk3;
+  // Fused Mixup: the partner's cells of this pass (4 rows x n_cols) are pulled into L1 now, a whole pass ahead of the
+  // epilogue that reads them
+  if (!STATS && p.mix_bank != nullptr) {                                                // [phase: mixup_prefetch]
+    const int j = __ldg(p.mix_partner + b);
+    if (j >= 0 && t0 < row_end) {
+      const float* mb = p.mix_bank + (size_t)j * p.out_frames * p.n_cols + (p.layout == 0 ? (size_t)t0 * p.n_cols : (size_t)t0);
+      if (p.layout == 0) {
+        const int r = lane >> 3, c = (lane & 7) * 32;                                  // 4 rows x up to 8 lines of 128 B
+        if (c < p.n_cols && t0 + r < row_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + (size_t)r * p.n_cols + c));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < fp.mel_groups && L.bin(i) >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + L.bin(i)));
+      }
+    }
+  }
   if (f0 < nf) {
     const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
     // the two packed transforms (frames 0,1 and 2,3); unrolled so their dependency chains interleave (a rolled loop
@@ -384,6 +400,18 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
                              : p.out + (p.layout == 0 ? ((size_t)b * p.out_frames + t0) * p.n_cols : (size_t)b * p.n_cols * p.out_frames + t0);
   // warp-uniform fast path: four live frames inside the segment and no time mask touching them
   const bool plain = (f0 + 4 <= nf) && (t0 + 4 <= row_end) && (mk1 <= 0 || t0 + 4 <= mk0 || t0 >= mk0 + mk1);
+  // fused Mixup: partner cells sit at the same offsets of the partner's spectrogram (re-read per pass: L1 hits, no registers
+  // held across the transform)
+  const float* mbase = nullptr;
+  float mlam = 1.f, moml = 0.f;
+  if (!STATS && p.mix_bank != nullptr) {
+    const int j = __ldg(p.mix_partner + b);
+    if (j >= 0) {
+      mlam = __ldg(p.mix_lam + b);
+      moml = __fsub_rn(1.0f, mlam);
+      mbase = p.mix_bank + (size_t)j * p.out_frames * p.n_cols + (p.layout == 0 ? (size_t)t0 * p.n_cols : (size_t)t0);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= fp.mel_groups) continue;
@@ -424,8 +452,16 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         float* o = obase + moff;
         if (plain) {
           const fk_u64 sc2 = fk_pk(L.scale(i), L.scale(i)), sh2 = fk_pk(L.shift(i), L.shift(i));
-          const float2 y01 = fk_upk(fk_fma2(fk_pk(v[0], v[1]), sc2, sh2)), y23 = fk_upk(fk_fma2(fk_pk(v[2], v[3]), sc2, sh2));
-          o[0] = y01.x; o[ostep] = y01.y; o[2 * ostep] = y23.x; o[3 * ostep] = y23.y;
+          float2 y01 = fk_upk(fk_fma2(fk_pk(v[0], v[1]), sc2, sh2)), y23 = fk_upk(fk_fma2(fk_pk(v[2], v[3]), sc2, sh2));
+          if (mbase != nullptr) {                                                        // [phase: mixup_epilogue]
+            const float* q = mbase + moff;
+            const float q0 = __ldg(q), q1 = __ldg(q + ostep), q2 = __ldg(q + 2 * ostep), q3 = __ldg(q + 3 * ostep);
+            y01.x = __fadd_rn(__fmul_rn(mlam, y01.x), __fmul_rn(moml, q0));
+            y01.y = __fadd_rn(__fmul_rn(mlam, y01.y), __fmul_rn(moml, q1));
+            y23.x = __fadd_rn(__fmul_rn(mlam, y23.x), __fmul_rn(moml, q2));
+            y23.y = __fadd_rn(__fmul_rn(mlam, y23.y), __fmul_rn(moml, q3));
+          }
+          o[0] = y01.x; o[ostep] = y01.y; o[2 * ostep] = y23.x; o[3 * ostep] = y23.y;   // [phase: epilogue_store]
         } else {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -434,6 +470,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
               // H9: pad rows are 0.0 before normalisation = the folded shift
               float y = (f0 + h) < nf ? fmaf(v[h], L.scale(i), L.shift(i)) : L.shift(i);
               if (t >= mk0 && t < mk0 + mk1) y = 0.f;
+              if (mbase != nullptr) y = __fadd_rn(__fmul_rn(mlam, y), __fmul_rn(moml, __ldg(mbase + moff + h * ostep)));
               o[h * ostep] = y;
             }
           }

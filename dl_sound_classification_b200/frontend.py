@@ -154,7 +154,7 @@ class FbankFrontend:
                  mean: Union[None, float, torch.Tensor] = None, std: Union[None, float, torch.Tensor] = None,
                  target_mean: float = 0.0, target_std: float = 0.5, layout: str = "btf",
                  out: Optional[torch.Tensor] = None, return_n_frames: bool = True, per_clip_norm: bool = False,
-                 remove_clip_mean: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                 remove_clip_mean: bool = False, mixup=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """The fused path (``b200fbank_execute``).  ``mean``/``std``: None (no
         normalisation), scalar, or per-column ``[n_cols]``; output
         ``(x-mean)/std*target_std+target_mean``.  ``masks``: int32 ``(B, 4)`` =
@@ -162,7 +162,10 @@ class FbankFrontend:
         ``per_clip_norm``: every clip is normalised with its OWN mean / unbiased std over its real frames instead
         (``b200fbank_clip_normalize``, the reference's src/datasets/preprocessing.py:1030-1037), masks after it.
         ``remove_clip_mean``: ``waveform - waveform.mean()`` per clip before the resampler
-        (``b200fbank_remove_clip_mean``; the AST recipe's convention)."""
+        (``b200fbank_remove_clip_mean``; the AST recipe's convention).
+        ``mixup``: ``(bank, plan)`` -- Mixup fused into the kernel's epilogue (``b200fbank_execute_mixup``): ``bank`` holds
+        spectrograms shaped like the output (same layout and ``out_frames``), ``plan`` is a ``mixup.MixupPlan``; the result
+        is bit-identical to ``mixup.mixup_batch`` applied to the un-mixed output, without the extra pass over the batch."""
         wav, off, clip, rid, B = self._wave_args(wav, offsets, rate_ids)
         if per_clip_norm and mean is not None:
             raise ValueError("per_clip_norm uses each clip's own statistics: do not pass mean/std")
@@ -192,16 +195,35 @@ class FbankFrontend:
             if mt.numel() != st.numel():
                 raise ValueError("mean and std must have the same number of elements")
             n_stats = int(mt.numel())
+        bank = partner = lam = None
+        if mixup is not None:
+            bank, plan = mixup
+            if bank.dtype != torch.float32 or tuple(bank.shape[1:]) != shape[1:]:
+                raise ValueError(f"the mixup bank must be float32 (N, {', '.join(map(str, shape[1:]))}), got {tuple(bank.shape)}")
+            bank = self._dev(bank, torch.float32, "mixup bank")
+            partner = self._dev(plan.partner, torch.int32, "mixup partner")
+            lam = self._dev(plan.lam, torch.float32, "mixup lam")
+            if int(partner.numel()) != B or int(lam.numel()) != B:
+                raise ValueError("the mixup plan does not match the batch")
+            if B and int(partner.max()) >= bank.shape[0]:
+                raise IndexError("partner index outside the bank")
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            K.check(K.lib.b200fbank_execute(
-                self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B,
-                None if per_clip_norm else self._ptr(mk),
-                self._ptr(mt), self._ptr(st), n_stats, float(target_mean), float(target_std), int(out_frames), lay,
-                out.data_ptr(), self._ptr(nfr), stream))
+            fused_mix = bank is not None and not per_clip_norm
+            head = (self.plan.handle, wav.data_ptr(), self._ptr(off), clip, self._ptr(rid), B,
+                    None if per_clip_norm else self._ptr(mk),
+                    self._ptr(mt), self._ptr(st), n_stats, float(target_mean), float(target_std), int(out_frames), lay)
+            if fused_mix:
+                K.check(K.lib.b200fbank_execute_mixup(*head, bank.data_ptr(), partner.data_ptr(), lam.data_ptr(),
+                                                      out.data_ptr(), self._ptr(nfr), stream))
+            else:
+                K.check(K.lib.b200fbank_execute(*head, out.data_ptr(), self._ptr(nfr), stream))
             if per_clip_norm and B > 0:
                 K.check(K.lib.b200fbank_clip_normalize(out.data_ptr(), nfr.data_ptr(), B, int(out_frames), self.n_cols, lay,
                                                        None, -1.0, 1, float(target_mean), float(target_std), self._ptr(mk), stream))
+                if bank is not None:       # per-clip statistics need the whole clip first: Mixup follows as its own launch
+                    K.check(K.lib.b200fbank_mixup(out.data_ptr(), bank.data_ptr(), partner.data_ptr(), lam.data_ptr(), B,
+                                                  int(out_frames) * self.n_cols, out.data_ptr(), stream))
         return out, (nfr if return_n_frames else None)
 
     def pcm16_to_float(self, pcm: torch.Tensor, divisor: Optional[torch.Tensor] = None,

@@ -23,7 +23,7 @@ import random
 from abc import ABC, abstractmethod
 from functools import lru_cache
 from pathlib import Path
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -218,9 +218,11 @@ class ASTPreprocessor(BasePreprocessor):
 
     # ------------------------------------------------------------------------------------------
     def preprocess_batch(self, waveforms: torch.Tensor, sample_rate, lengths: Optional[Sequence[int]] = None,
-                         masks: Optional[torch.Tensor] = None, target_frames: Optional[int] = None):
+                         masks: Optional[torch.Tensor] = None, target_frames: Optional[int] = None, mixup=None):
         """``(B, N)`` (or flat ragged + ``lengths``) -> ``((B, 1, n_mels, T), n_frames[B])`` on the GPU.
-        ``sample_rate`` is an int or a per-clip sequence drawn from the plan's rate table."""
+        ``sample_rate`` is an int or a per-clip sequence drawn from the plan's rate table.  ``mixup`` = ``(bank, plan)``
+        (``mixup.draw_mixup_plan``): Mixup after SpecAugment as in esc50.py:267-285 -- fused into the kernel's epilogue
+        for the kaldi recipe with dataset statistics, one more launch otherwise; same bits either way."""
         fe = self.frontend
         if isinstance(sample_rate, int):
             rid_list = None if fe.rate_id(sample_rate) == 0 and len(fe.orig_rates) == 1 else None
@@ -247,9 +249,13 @@ class ASTPreprocessor(BasePreprocessor):
                 raise AssertionError("choose a window size {} that is [2, {}]".format(fe.plan.window_size, min(max_len)))
         if self.frontend_name == "melspectrogram":
             # src/datasets/preprocessing.py:1024-1037: dB, top_db clamp and per-clip normalisation are fused passes
-            return fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids, masks=masks, to_db=True,
-                      normalize=bool(self.normalize), target_mean=self.target_mean, target_std=self.target_std,
-                      layout="bft")
+            out, nfr = fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids, masks=masks, to_db=True,
+                          normalize=bool(self.normalize), target_mean=self.target_mean, target_std=self.target_std,
+                          layout="bft")
+            if mixup is not None:
+                from .mixup import mixup_batch
+                out = mixup_batch(out, mixup[0], mixup[1], out=out)
+            return out, nfr
         mean = std = None
         if self.normalize and self.norm_mean is not None:
             mean, std = self.norm_mean, self.norm_std
@@ -257,7 +263,7 @@ class ASTPreprocessor(BasePreprocessor):
         # (src/datasets/preprocessing.py:1030-1037): one more kernel pass on the device, masks after it
         per_clip = bool(self.normalize and self.norm_mean is None)
         return fe(waveforms, out_frames=int(T), offsets=offsets, rate_ids=rate_ids, masks=masks, mean=mean, std=std,
-                  target_mean=self.target_mean, target_std=self.target_std, layout="bft", per_clip_norm=per_clip)
+                  target_mean=self.target_mean, target_std=self.target_std, layout="bft", per_clip_norm=per_clip, mixup=mixup)
 
     def preprocess(self, waveform: torch.Tensor, sample_rate: int) -> torch.Tensor:
         if waveform.dim() == 1:
@@ -351,6 +357,83 @@ class PreprocessingCache:
         pre.setup_cache(self.base_cache_dir, force_rebuild=force_rebuild, max_cache_size_gb=self.max_cache_size_gb)
         self.preprocessors[key] = pre
         return pre
+
+    def batch_preprocess(self, file_paths: List[Path], mode: str, config: PreprocessingConfig, num_workers: int = 4,
+                         show_progress: bool = True, batch_clips: int = 256, sample_rate: int = 44100,
+                         use_cache: bool = True) -> List[torch.Tensor]:
+        """src/datasets/preprocessing.py:1176-1254 with the same signature and result: the preprocessed tensors
+        ``[1, n_mels, T_clip]`` (CPU, float32) of the files that could be loaded, in file order, files that fail to load
+        skipped with a warning.  The reference runs ``preprocess_with_cache`` per file on a thread pool; here the
+        ``num_workers`` threads only LOAD the ``.pt`` bundles (``load_audio_bundle``, :100-117: ``{"waveform", "label"}``,
+        44.1 kHz assumed as at :1205) while the features of ``batch_clips`` clips at a time come from ONE ragged fused
+        launch.  With ``use_cache`` the reference's own cache files are read first and written for the misses, as
+        ``preprocess_with_cache`` does (:733-764)."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import cache as _cache
+        pre = self.setup_preprocessor(mode, config)
+        cache_dir = getattr(pre, "cache_dir", None) if use_cache else None
+        config_hash = config.get_hash()
+        paths = [Path(f) for f in file_paths]
+        results: List[Optional[torch.Tensor]] = [None] * len(paths)
+
+        def load(i: int):
+            try:
+                if cache_dir is not None:
+                    hit = _cache.read_cache_entry(cache_dir, paths[i], config_hash)
+                    if hit is not None:
+                        return i, hit, True
+                bundle = torch.load(paths[i], map_location="cpu")
+                return i, bundle["waveform"], False
+            except Exception as e:                               # the reference logs and skips (:1214-1216)
+                logger.warning(f"Failed to process {paths[i]}: {e}")
+                return i, None, False
+
+        bar = None
+        if show_progress:
+            try:
+                from tqdm import tqdm
+                bar = tqdm(total=len(paths), desc=f"Preprocessing with {mode}", unit="files")
+            except ImportError:
+                bar = None
+        pending: List[Tuple[int, torch.Tensor]] = []
+        entries: List[Tuple[Path, Path]] = []
+
+        def flush():
+            if not pending:
+                return
+            waves = [w.reshape(-1).to(torch.float32) for _, w in pending]
+            out, nfr = pre.preprocess_batch(torch.cat(waves), int(sample_rate), lengths=[int(w.numel()) for w in waves])
+            out, nfr = out.cpu(), nfr.cpu().tolist()
+            for (i, _), feats, m in zip(pending, out, nfr):
+                if int(m) <= 0:
+                    logger.warning(f"Failed to process {paths[i]}: clip is shorter than one analysis window")
+                    continue
+                results[i] = feats[..., :int(m)].clone()
+                if cache_dir is not None:
+                    entries.append((paths[i], _cache.write_cache_entry(cache_dir, paths[i], config_hash, results[i])))
+            pending.clear()
+
+        loader = ThreadPoolExecutor(max_workers=max(1, int(num_workers)))
+        try:
+            for i, data, hit in loader.map(load, range(len(paths))):
+                if bar is not None:
+                    bar.update(1)
+                if data is None:
+                    continue
+                if hit:
+                    results[i] = data
+                    continue
+                pending.append((i, data))
+                if len(pending) >= batch_clips:
+                    flush()
+            flush()
+        finally:
+            loader.shutdown()
+            if bar is not None:
+                bar.close()
+        if entries:
+            _cache._update_metadata(cache_dir, entries, config_hash)
+        return [r for r in results if r is not None]
 
 
 def create_preprocessor(mode: str, config_dict: Dict[str, Any], base_cache_dir: Path, force_rebuild: bool = False,

@@ -168,6 +168,26 @@ int b200fbank_execute(const b200fbank_plan* p, const float* d_wav, const int64_t
                       float* d_out, int32_t* d_n_frames, void* stream);
 
 /*
+ * b200fbank_execute with Mixup fused into the epilogue (SURVEY.md section 8f N3 moved into the producing kernel): after
+ * normalisation and the SpecAugment zero-fill -- the reference's order, src/datasets/esc50.py:267-285 -- clip b becomes
+ * lam[b] * y + (1 - lam[b]) * bank[partner[b]] with the three float32 roundings of MixupAugmentation.__call__
+ * (src/datasets/preprocessing.py:960, csrc/mixup.cuh), pad rows included (the reference mixes whole tensors), so the
+ * result is bit-identical to b200fbank_execute followed by b200fbank_mixup while the batch is written once instead of
+ * written, re-read and written again.
+ *  d_bank      (N, out_frames, n_cols) or (N, 1, n_cols, out_frames) float32 spectrograms in the SAME layout and
+ *              out_frames as d_out (the reference's `_cached_data`, esc50.py:280-282); must not alias d_out
+ *  d_partner   [B] index into the bank, < 0: the clip is left alone
+ *  d_lam       [B] mixing coefficients
+ * Plans that run on the generic kernel (or with subtract_mean) mix with a second launch, same result.
+ */
+int b200fbank_execute_mixup(const b200fbank_plan* p, const float* d_wav, const int64_t* d_offsets,
+                            int64_t clip_samples, const int32_t* d_rate_id, int B,
+                            const int32_t* d_masks, const float* d_mean, const float* d_std, int n_stats,
+                            float target_mean, float target_std, int out_frames, int layout,
+                            const float* d_bank, const int32_t* d_partner, const float* d_lam,
+                            float* d_out, int32_t* d_n_frames, void* stream);
+
+/*
  * The reference-ACTUAL recipe on a MELSPEC_DB plan: resample-if-needed ->
  * MelSpectrogram(n_fft, win_length, hop_length, power=2, center, reflect, periodic Hann, HTK mel, norm=None)
  * -> AmplitudeToDB(top_db) -> per-clip (x - mean) / unbiased_std * target_std + target_mean.  Replaces

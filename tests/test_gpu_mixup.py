@@ -74,3 +74,53 @@ def test_mixup_full_size_properties(b2):
         assert np.array_equal(out[i].cpu().numpy(), ref), i
     with pytest.raises(IndexError):
         b2.mixup_batch(x[:2], bank[:5], b2.MixupPlan(torch.tensor([1, 9], dtype=torch.int32), torch.ones(2)))
+
+
+@pytest.mark.parametrize("layout", ["btf", "bft"])
+def test_mixup_fused_into_the_fbank_epilogue_is_bit_identical(b2, layout):
+    """b200fbank_execute_mixup == b200fbank_execute followed by b200fbank_mixup, bit for bit: dense batch with
+    normalisation, SpecAugment masks and pad rows (both layouts), partner -1 rows untouched."""
+    from inputs import config1_clips
+    Bq, T = 12, 320                                                        # 2 s clips -> 198 real frames + pad rows
+    wav = torch.cat(config1_clips(Bq, seed=7, length=88200), 0).cuda()
+    fe = b2.FbankFrontend(orig_rates=(44100,), **b2.AST_FBANK_KWARGS)
+    random.seed(3)
+    torch.manual_seed(3)
+    masks = b2.specaugment.draw_masks(Bq, T, 128, 48, 24, variant="reference")
+    bank_wav = torch.cat(config1_clips(5, seed=70, length=88200), 0).cuda()
+    bank, _ = fe(bank_wav, out_frames=T, mean=-4.27, std=4.57, layout=layout)
+    plan = b2.draw_mixup_plan(Bq, 5, alpha=0.5, prob=0.9)
+    assert int((plan.partner >= 0).sum()) >= 2 and int((plan.partner < 0).sum()) >= 2
+    plain, nfr = fe(wav, out_frames=T, masks=masks, mean=-4.27, std=4.57, layout=layout)
+    want = b2.mixup_batch(plain, bank, plan)
+    got, nfr2 = fe(wav, out_frames=T, masks=masks, mean=-4.27, std=4.57, layout=layout, mixup=(bank, plan))
+    assert torch.equal(nfr, nfr2) and int(nfr[0]) == 198
+    assert torch.equal(got, want)
+    keep = plan.partner < 0
+    assert torch.equal(got[keep.cuda()], plain[keep.cuda()])
+    # per-clip statistics: the mix follows the normalisation pass as its own launch, same bits
+    a, _ = fe(wav, out_frames=T, masks=masks, layout=layout, per_clip_norm=True)
+    b_, _ = fe(wav, out_frames=T, masks=masks, layout=layout, per_clip_norm=True, mixup=(bank, plan))
+    assert torch.equal(b_, b2.mixup_batch(a, bank, plan))
+    with pytest.raises(ValueError):
+        fe(wav, out_frames=T, mixup=(bank[:, ..., :-1].contiguous(), plan))
+
+
+def test_mixup_fused_ragged_multi_rate_batch(b2):
+    """The dynamic persistent launch (ragged clips, three rates) with the fused mix."""
+    from inputs import us8k_small_clips
+    clips, rates = us8k_small_clips(9)
+    table = (22050, 44100, 48000)
+    lens = torch.tensor([c.shape[1] for c in clips])
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    flat = torch.cat([c[0] for c in clips]).cuda()
+    rid = torch.tensor([table.index(r) for r in rates], dtype=torch.int32)
+    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    T = 416
+    bank = torch.randn(4, 1, 128, T, generator=torch.Generator().manual_seed(2)).cuda()
+    random.seed(9)
+    torch.manual_seed(9)
+    plan = b2.draw_mixup_plan(9, 4, alpha=0.5, prob=1.0)
+    plain, _ = fe(flat, out_frames=T, offsets=offsets, rate_ids=rid, mean=-4.27, std=4.57, layout="bft")
+    got, _ = fe(flat, out_frames=T, offsets=offsets, rate_ids=rid, mean=-4.27, std=4.57, layout="bft", mixup=(bank, plan))
+    assert torch.equal(got, b2.mixup_batch(plain, bank, plan))

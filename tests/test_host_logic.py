@@ -253,3 +253,55 @@ def test_stats_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_datamodule_mixin_draw_order_and_passthrough(monkeypatch):
+    """CPU: the mixin consumes Python's `random` per sample in the reference's order (SpecAugment's four randints, then
+    Mixup's coin / partner / coin), and leaves spectrogram batches alone.  The device work is stubbed out."""
+    import random
+    import types
+    import dl_sound_classification_b200.datamodule as DMOD
+    from dl_sound_classification_b200 import specaugment as SA
+
+    seen = {}
+
+    class StubPre:
+        n_mels, sample_rate, target_frames = 128, 44100, 276
+        frontend = None
+
+        def preprocess_batch(self, wav, sr, masks=None, target_frames=None, mixup=None):
+            seen["masks"], seen["plan"] = masks, mixup[1]
+            return torch.zeros(wav.shape[0], 1, 128, target_frames), None
+
+    monkeypatch.setattr(DMOD, "mixup_labels", lambda hard, bl, plan, n: torch.zeros(hard.shape[0], n))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+
+    class DM(DMOD.B200DataModuleMixin):
+        sample_rate, num_classes, time_mask, freq_mask, enable_mixup, mixup_alpha = 44100, 50, True, 48, True, 0.5
+        trainer = types.SimpleNamespace(training=True)
+
+    dm = DM()
+    dm.setup_b200(preprocessor=StubPre())
+    dm.set_mixup_bank(torch.zeros(9, 1, 128, 276), torch.arange(9))
+    B = 5
+    random.seed(11)
+    torch.manual_seed(11)
+    spec, soft = dm.on_after_batch_transfer((torch.zeros(B, 1, 1000), torch.arange(B)), 0)
+    assert tuple(spec.shape) == (B, 1, 128, 276) and tuple(soft.shape) == (B, 50)
+    random.seed(11)
+    torch.manual_seed(11)
+    rows, partners = [], []
+    for _ in range(B):
+        rows.append(list(SA.reference_intervals(276, 128, 192, 48, random)))
+        p = -1
+        if not random.random() > 0.5:
+            other = random.randint(0, 8)
+            if not random.random() > 0.5:
+                p = other
+                torch.distributions.Beta(0.5, 0.5).sample()
+        partners.append(p)
+    assert seen["masks"].tolist() == rows
+    assert seen["plan"].partner.tolist() == partners
+    b4 = (torch.zeros(2, 1, 128, 276), torch.zeros(2, 50))
+    assert dm.on_after_batch_transfer(b4, 0) is b4
