@@ -27,6 +27,7 @@
 #include "clip_norm.cuh"
 #include "melspec_fast.cuh"
 #include "patch_embed.cuh"
+#include "patch_embed_pipe.cuh"
 #include <cstdlib>
 
 namespace {
@@ -837,6 +838,9 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     B200_WS_ATTR(false, false, false); B200_WS_ATTR(false, true, false); B200_WS_ATTR(true, false, false); B200_WS_ATTR(true, true, false);
     B200_WS_ATTR(false, false, true); B200_WS_ATTR(false, true, true); B200_WS_ATTR(true, false, true); B200_WS_ATTR(true, true, true);
 #undef B200_WS_ATTR
+#define B200_WS_ATTR_MIX(A, M) CUDA_TRY(cudaFuncSetAttribute(b200::fbank_ws_kernel<false, A, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin))
+    B200_WS_ATTR_MIX(false, false); B200_WS_ATTR_MIX(true, false); B200_WS_ATTR_MIX(false, true); B200_WS_ATTR_MIX(true, true);
+#undef B200_WS_ATTR_MIX
   }
   const char* seg = getenv("B200FBANK_SEG");
   f.seg_frames = seg ? std::max(32, atoi(seg) / 32 * 32) : 0;      // 0 = pick per launch (pick_seg_frames)
@@ -1074,7 +1078,7 @@ static int execute_impl(const b200fbank_plan* p, const float* d_wav, const int64
   // Mixup rides in the epilogue of the tuned kernels; the generic kernel (and CMS, which finishes in a second kernel)
   // mix with one more launch of the stand-alone mixup kernel, in place
   const bool mix = d_bank != nullptr;
-  const bool mix_fused = mix && p->fast_ok && !cms;
+  const bool mix_fused = mix && p->fast_ok && p->ws_ok && !cms;
   if (mix_fused) { k.mix_bank = d_bank; k.mix_partner = d_partner; k.mix_lam = d_lam; }
   if (p->fast_ok && p->ws_ok) {
     b200::FastParams f = p->fast;
@@ -1083,7 +1087,15 @@ static int execute_impl(const b200fbank_plan* p, const float* d_wav, const int64
     int64_t grid = (int64_t)B * f.segs;
     if (grid > 0x7fffffffLL) return fail(B200FBANK_ERR_INVALID, "B * segments = %lld exceeds the grid limit", (long long)grid);
     if (int rc = ws_pick_grid(p, d_offsets, f, grid, st)) return rc;
-    if (f.ws_multi) {
+    if (mix_fused) {
+      if (f.ws_multi) {
+        if (f.ast_bank) b200::fbank_ws_kernel<false, true, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+        else b200::fbank_ws_kernel<false, false, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+      } else {
+        if (f.ast_bank) b200::fbank_ws_kernel<false, true, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+        else b200::fbank_ws_kernel<false, false, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
+      }
+    } else if (f.ws_multi) {
       if (f.ast_bank) b200::fbank_ws_kernel<false, true, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
       else b200::fbank_ws_kernel<false, false, true><<<(unsigned)grid, b200::WS_THREADS, p->ws_smem, st>>>(k, f);
     } else {
@@ -1387,6 +1399,46 @@ int b200fbank_patch_embed(const float* d_feat, int B, int F, int T, const void* 
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int NT = D / b200::PE_N;
+  // The TMA + tcgen05 pipeline (patch_embed_pipe.cuh) needs a tensor map over the features: rows of T floats with a
+  // 16-byte aligned pitch and base.  Anything else (and B200FBANK_PE=gather) runs the gather kernel below.
+  static const bool force_gather = [] { const char* e = getenv("B200FBANK_PE"); return e && !strcmp(e, "gather"); }();
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) fn = nullptr;
+    return (EncodeFn)fn;
+  }();
+  const int seg_cap = std::min(b200::PP_SEG, (2 * b200::PP_BOXW - 3 - patch) / stride + 1);
+  if (!force_gather && encode && seg_cap >= 1 && T % 4 == 0 && ((uintptr_t)d_feat & 15) == 0 && ((uintptr_t)d_out & 15) == 0 &&
+      (int64_t)B * F < (1ll << 31)) {
+    const int nseg = (k.Tp + seg_cap - 1) / seg_cap, segp = (k.Tp + nseg - 1) / nseg;
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)B * (cuuint64_t)F};
+    const cuuint64_t strides[1] = {(cuuint64_t)T * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)b200::PP_BOXW, 4}, estr[2] = {1, 1};
+    const CUresult er = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_feat), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (er != CUDA_SUCCESS) return fail(B200FBANK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)er);
+    const int64_t n_tiles = ((int64_t)B * k.Fp * nseg + 1) / 2;
+    const int per_col = (int)std::min<int64_t>(n_tiles, std::max(1, sms / NT));
+    static std::atomic<unsigned long long> pipe_attr_done{0};
+    if (dev >= 64 || !((pipe_attr_done.load() >> dev) & 1ull)) {
+      CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PP_SMEM));
+      CUDA_TRY(cudaFuncSetAttribute(b200::patch_embed_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b200::PP_SMEM));
+      if (dev < 64) pipe_attr_done.fetch_or(1ull << dev);
+    }
+    const unsigned pgrid = (unsigned)(per_col * NT);
+    if (out_f16) b200::patch_embed_pipe_kernel<true><<<pgrid, b200::PP_THREADS, b200::PP_SMEM, (cudaStream_t)stream>>>(k, nseg, segp, tm);
+    else b200::patch_embed_pipe_kernel<false><<<pgrid, b200::PP_THREADS, b200::PP_SMEM, (cudaStream_t)stream>>>(k, nseg, segp, tm);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   const int64_t m_tiles = (k.M + b200::PE_M - 1) / b200::PE_M;
   int per_col = (int)std::min<int64_t>(m_tiles, std::max(1, sms / NT));
   const unsigned grid = (unsigned)(per_col * NT);

@@ -319,7 +319,7 @@ __device__ __forceinline__ void fk_mel_group(const float4* __restrict__ P4, cons
 // `rows` (ring rows of stride RS; 6 rows are touched) -> 4 x n_mel outputs.  n_live = how many of the four are
 // real frames (the rest are pad rows).  Ebuf = this warp's FK_EBUF floats.  AST = compile-time filter lengths
 // (2,3,6,10) of the AST bank.
-template <bool STATS, bool AST, int RS, class LC>
+template <bool STATS, bool AST, int RS, class LC, bool MIX = false>   // MIX: Mixup fused into the epilogue (own instantiation: the plain kernels carry none of its code)
 __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastParams& fp, const LC& L,
                                               const float* __restrict__ rows, float* __restrict__ Ebuf,
                                               const float2* __restrict__ stw, const float* __restrict__ smelw,
@@ -332,7 +332,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   (void)mk2; (void)mk3;
   // Fused Mixup: the partner's cells of this pass (4 rows x n_cols) are pulled into L1 now, a whole pass ahead of the
   // epilogue that reads them
-  if (!STATS && p.mix_bank != nullptr) {                                                // [phase: mixup_prefetch]
+  if (MIX && !STATS && p.mix_bank != nullptr) {                                         // [phase: mixup_prefetch]
     const int j = __ldg(p.mix_partner + b);
     if (j >= 0 && t0 < row_end) {
       const float* mb = p.mix_bank + (size_t)j * p.out_frames * p.n_cols + (p.layout == 0 ? (size_t)t0 * p.n_cols : (size_t)t0);
@@ -404,7 +404,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
   // held across the transform)
   const float* mbase = nullptr;
   float mlam = 1.f, moml = 0.f;
-  if (!STATS && p.mix_bank != nullptr) {
+  if (MIX && !STATS && p.mix_bank != nullptr) {
     const int j = __ldg(p.mix_partner + b);
     if (j >= 0) {
       mlam = __ldg(p.mix_lam + b);
@@ -453,7 +453,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
         if (plain) {
           const fk_u64 sc2 = fk_pk(L.scale(i), L.scale(i)), sh2 = fk_pk(L.shift(i), L.shift(i));
           float2 y01 = fk_upk(fk_fma2(fk_pk(v[0], v[1]), sc2, sh2)), y23 = fk_upk(fk_fma2(fk_pk(v[2], v[3]), sc2, sh2));
-          if (mbase != nullptr) {                                                        // [phase: mixup_epilogue]
+          if (MIX && mbase != nullptr) {                                                 // [phase: mixup_epilogue]
             const float* q = mbase + moff;
             const float q0 = __ldg(q), q1 = __ldg(q + ostep), q2 = __ldg(q + 2 * ostep), q3 = __ldg(q + 3 * ostep);
             y01.x = __fadd_rn(__fmul_rn(mlam, y01.x), __fmul_rn(moml, q0));
@@ -470,7 +470,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
               // H9: pad rows are 0.0 before normalisation = the folded shift
               float y = (f0 + h) < nf ? fmaf(v[h], L.scale(i), L.shift(i)) : L.shift(i);
               if (t >= mk0 && t < mk0 + mk1) y = 0.f;
-              if (mbase != nullptr) y = __fadd_rn(__fmul_rn(mlam, y), __fmul_rn(moml, __ldg(mbase + moff + h * ostep)));
+              if (MIX && mbase != nullptr) y = __fadd_rn(__fmul_rn(mlam, y), __fmul_rn(moml, __ldg(mbase + moff + h * ostep)));
               o[h * ostep] = y;
             }
           }

@@ -199,6 +199,7 @@ __device__ __forceinline__ WsItem ws_item(const FbankParams& p, const FastParams
   return it;
 }
 
+// MIX: Mixup fused into the epilogue (b200fbank_execute_mixup).
 // MULTI: the 48 kHz / 22.05 kHz resampler modes are compiled in (plans whose rate table needs them); single-rate
 // 44.1 kHz plans run the lean instantiation.
 //
@@ -206,7 +207,7 @@ __device__ __forceinline__ WsItem ws_item(const FbankParams& p, const FastParams
 // runs straight through the item boundaries (ring slots, barrier phases and the pass -> warp assignment are numbered
 // per CTA, not per clip), so the R warps resample the head of the next clip while the F warps still finish the tail of
 // the current one.  Otherwise grid = #items and every CTA takes exactly one.
-template <bool STATS, bool AST, bool MULTI>
+template <bool STATS, bool AST, bool MULTI, bool MIX = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankParams p, const FastParams fp) {   // [phase: ws_setup]
   extern __shared__ __align__(16) float smem[];
   float* xbuf = smem;                                            // [WS_XFLOATS] input chunk (R warps only)
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           WS_TACC(4, tf0_);
 #endif
           const int row = (row0 + 4 * pp) % WS_RING_ROWS;
-          fk_frame_pass<STATS, AST, FK_SHIFT, FkLane>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, it.row_end, lane,
+          fk_frame_pass<STATS, AST, FK_SHIFT, FkLane, MIX>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, it.row_end, lane,
                                               mk0, mk1, mk2, mk3, st_s, st_ss);
 #ifdef B200_WS_TIMING
           WS_TACC(5, tf1_); if (lane == 0) atomicAdd(&g_ws_timing[6], 1ull);

@@ -372,6 +372,8 @@ class PreprocessingCache:
         from . import cache as _cache
         pre = self.setup_preprocessor(mode, config)
         cache_dir = getattr(pre, "cache_dir", None) if use_cache else None
+        if cache_dir is not None:
+            Path(cache_dir).mkdir(parents=True, exist_ok=True)
         config_hash = config.get_hash()
         paths = [Path(f) for f in file_paths]
         results: List[Optional[torch.Tensor]] = [None] * len(paths)

@@ -78,3 +78,31 @@ def test_full_size_feeds_from_the_frontend(b2):
         b2.patch_embed(spec[:1], torch.zeros(100, 1, 16, 16), None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         b2.patch_embed(spec[:1].cpu(), conv.weight, conv.bias)
+
+
+@pytest.mark.parametrize("B,F,T,D,stride", [(2, 128, 1024, 192, 10),      # three segments per patch row
+                                            (1, 36, 1380, 384, 10),        # odd number of segments (tail tile half empty), mel-dB length
+                                            (3, 128, 512, 192, 16),        # non-overlapping patches
+                                            (2, 64, 300, 192, 7),          # odd stride: 32-bit strip reads
+                                            (1, 128, 2048, 192, 10)])
+def test_tma_pipeline_shapes_against_torch_convolution(b2, B, F, T, D, stride):
+    """The TMA + tcgen05 pipeline (patch_embed_pipe.cuh; taken whenever T % 4 == 0) on segmentations the AST shape does
+    not reach: several segments per patch row, a half-empty tail tile, other strides and heights, both output types."""
+    torch.manual_seed(B * 7 + T + D + stride)
+    x = (torch.randn(B, 1, F, T) * 0.5).cuda()
+    conv = torch.nn.Conv2d(1, D, 16, stride=stride).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref16 = torch.nn.functional.conv2d(x.half().float(), conv.weight.half().float(), conv.bias,
+                                               stride=stride).flatten(2).transpose(1, 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    got = b2.patch_embed(x, conv.weight, conv.bias, stride, torch.float32)
+    assert tuple(got.shape) == tuple(ref16.shape)
+    assert float((got - ref16).abs().max()) < ATOL_VS_FP16_OPERANDS
+    half = b2.patch_embed(x, conv.weight, conv.bias, stride, torch.float16)
+    assert float((half.float() - got).abs().max()) < 4e-3
+    # repeated launches on one stream (barrier phases start from scratch every launch)
+    assert torch.equal(b2.patch_embed(x, conv.weight, conv.bias, stride, torch.float32), got)
