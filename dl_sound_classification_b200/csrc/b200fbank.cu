@@ -1464,6 +1464,15 @@ extern "C" int b200fbank_debug_pe_timing(unsigned long long out[4]) {
 }
 #endif
 
+#ifdef B200_PP_TIMING
+extern "C" int b200fbank_debug_pp_timing(unsigned long long out[16]) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out, b200::g_pp_timing, sizeof z) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(b200::g_pp_timing, z, sizeof z);
+  return 0;
+}
+#endif
+
 int64_t b200fbank_launch_count(int reset) {
   int64_t n = g_launches;
   if (reset) g_launches = 0;

@@ -5,15 +5,17 @@
 // The patches of one patch row overlap (16 wide, stride 10), and their stride of 40 bytes cannot be expressed by a tensor-map
 // or a UMMA descriptor (both want multiples of 16 bytes), so the A operand is built in two steps:
 //   1. TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) pulls STRIPS of the feature map -- 4 feature rows x 512 frames of the
-//      16-row band a patch row covers -- into a 2-stage shared-memory ring; every feature byte of a tile crosses L2 -> SM once
+//      16-row band a patch row covers -- into a 4-stage shared-memory ring; every feature byte of a tile crosses L2 -> SM once
 //      instead of once per overlapping patch, fully coalesced, asynchronously.
 //   2. four "cutter" warps read the patches out of the strips (conflict-free 64-bit loads: lanes = consecutive patches,
-//      40 B apart), round to fp16 and write the K-major 128-byte-swizzled A chunk (128 rows x 64 taps) the tensor core reads.
+//      40 B apart), round to fp16 and store the A chunk (128 rows x 64 taps) straight into TENSOR MEMORY (tcgen05.st, SASS STTM:
+//      row = lane, two taps per 32-bit column); the MMA takes A from TMEM and only W from shared memory, which spares the
+//      shared-memory data path a write + a read of every A byte and the cutters the generic -> async proxy fence.
 // A tile = 2 segments of up to 64 patches of one patch row each (50 + 50 real rows of the 128 for AST's T = 512); its K = 256
 // is cut in four chunks of 4 feature rows, and the chunks are the unit of the pipeline:
 //
-//   warp 0      TMA producer: strips of chunk q + 1 are in flight while chunk q is being cut
-//   warps 8-11  cutters: strip stage -> A chunk ring (4 x 16 KB), release the strip stage
+//   warp 0      TMA producer: the strips of chunks q + 1 .. q + 3 are in flight while chunk q is being cut
+//   warps 8-11  cutters: strip stage -> A chunk slot in TMEM (2 slots of 32 columns), release the strip stage
 //   warp 1      MMA issuer: 4 x tcgen05.mma (M 128, N 192, K 16) per chunk, tcgen05.commit frees the A chunk; the
 //               accumulator (fp32, TMEM) is double buffered: tile k + 1 accumulates while tile k is drained
 //   warps 4-7   epilogue: tcgen05.ld -> + bias -> fp16 / fp32 -> per-warp staging rows -> contiguous 16-byte row segments
@@ -33,11 +35,36 @@ constexpr int PP_BOXW = 256;                             // floats per TMA box r
 constexpr int PP_BOX_BYTES = 4 * PP_BOXW * 4;            // 4 feature rows x 256 frames
 constexpr int PP_SEG_BYTES = 2 * PP_BOX_BYTES;           // two boxes: 512 frames of 4 rows
 constexpr int PP_STAGE_BYTES = 2 * PP_SEG_BYTES;         // two segments: 16 KB
-constexpr int PP_NSTAGE = 2;
+#ifndef B200_PP_NSTAGE
+#define B200_PP_NSTAGE 4
+#endif
+constexpr int PP_NSTAGE = B200_PP_NSTAGE;                // strip ring: the TMA latency (~1.5 k cycles) wants >= 48 KB in flight per SM
+constexpr int PP_NA = 2;                                 // A chunk slots (TMEM, 32 columns each): one being cut, one being multiplied
+constexpr int PP_ACOL0 = 192, PP_ACOL1 = 448;            // their columns: behind the two accumulators (0..191, 256..447)
 constexpr int PP_STG_ROW = 208;                          // staging row: 192 B + 16 B pad
 constexpr int PP_TMEM_COLS = 512;                        // two accumulators of 192 columns at 0 and 256
-constexpr size_t PP_SMEM = 1024 + (size_t)PE_NKB * (PE_A_KB_BYTES + PE_B_KB_BYTES) + PP_NSTAGE * PP_STAGE_BYTES +
+constexpr size_t PP_SMEM = 1024 + (size_t)PE_NKB * PE_B_KB_BYTES + PP_NSTAGE * PP_STAGE_BYTES +
                            4 * 32 * PP_STG_ROW + PE_N * 4 + 256;
+
+// Optional pipeline timing (-DB200_PP_TIMING): cycles summed over all CTAs into g_pp_timing[12] =
+// {producer wait s_empty, cutter wait s_full, cutter wait a_empty, cutter busy, mma wait a_full, mma wait acc_empty,
+//  epilogue wait acc_full, epilogue busy, tiles, -, -, -}
+#ifdef B200_PP_TIMING
+__device__ unsigned long long g_pp_timing[16];
+// (accumulated in registers and flushed once per role: a global atomic inside the loop would sit in front of the cutters'
+// memory fence and distort what it measures)
+#define PP_TDECL() unsigned long long tacc_[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull}
+#define PP_TW(i, stmt) do { const long long t_ = clock64(); stmt; tacc_[i] += (unsigned long long)(clock64() - t_); } while (0)
+#define PP_TADD(i, since) do { tacc_[i] += (unsigned long long)(clock64() - (since)); } while (0)
+#define PP_TFLUSH(i, slot) do { if (lane == 0) atomicAdd(&g_pp_timing[slot], tacc_[i]); } while (0)
+#define PP_NOW() clock64()
+#else
+#define PP_TDECL()
+#define PP_TW(i, stmt) stmt
+#define PP_TADD(i, since)
+#define PP_TFLUSH(i, slot)
+#define PP_NOW() 0ll
+#endif
 
 __device__ __forceinline__ void pp_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -55,18 +82,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
   const uint32_t raw = (uint32_t)__cvta_generic_to_shared(pe_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                         // SWIZZLE_128B tiles need 1024-B alignment
   uint8_t* gen = pe_smem_raw + (base - raw);
-  constexpr uint32_t OFF_A = PE_NKB * PE_B_KB_BYTES, OFF_S = OFF_A + PE_NKB * PE_A_KB_BYTES, OFF_STG = OFF_S + PP_NSTAGE * PP_STAGE_BYTES,
+  constexpr uint32_t OFF_S = PE_NKB * PE_B_KB_BYTES, OFF_STG = OFF_S + PP_NSTAGE * PP_STAGE_BYTES,
                      OFF_BIAS = OFF_STG + 4 * 32 * PP_STG_ROW, OFF_BAR = OFF_BIAS + PE_N * 4;
   uint8_t* sB = gen;                                                    // [4][192 rows x 128 B] weights
-  uint8_t* sA = gen + OFF_A;                                            // [4][128 rows x 128 B] A chunk ring
-  const uint8_t* sS = gen + OFF_S;                                      // [2 stages][2 segments][2 boxes][4 rows][256] fp32 strips
+  const uint8_t* sS = gen + OFF_S;                                      // [PP_NSTAGE][2 segments][2 boxes][4 rows][256] fp32 strips
   uint8_t* sStage = gen + OFF_STG;                                      // [4 warps][32 rows][208 B]
   float* sbias = reinterpret_cast<float*>(gen + OFF_BIAS);
-  const uint32_t sB_a = base, sA_a = base + OFF_A, sS_a = base + OFF_S, bar0 = base + OFF_BAR;
-  // barriers (8 B each): s_full[2] s_empty[2] a_full[4] a_empty[4] acc_full[2] acc_empty[2]; then the TMEM base address
-  const uint32_t s_full = bar0, s_empty = bar0 + 16, a_full = bar0 + 32, a_empty = bar0 + 64, acc_full = bar0 + 96, acc_empty = bar0 + 112;
-  const uint32_t tmem_slot_a = bar0 + 128;
-  const uint32_t* tmem_slot = reinterpret_cast<const uint32_t*>(gen + OFF_BAR + 128);
+  const uint32_t sB_a = base, sS_a = base + OFF_S, bar0 = base + OFF_BAR;
+  // barriers (8 B each): s_full[8] s_empty[8] a_full[2] a_empty[2] acc_full[2] acc_empty[2]; then the TMEM base address
+  static_assert(PP_NSTAGE <= 8 && PP_NA == 2, "barrier layout");
+  const uint32_t s_full = bar0, s_empty = bar0 + 64, a_full = bar0 + 128, a_empty = bar0 + 144, acc_full = bar0 + 160, acc_empty = bar0 + 176;
+  const uint32_t tmem_slot_a = bar0 + 192;
+  const uint32_t* tmem_slot = reinterpret_cast<const uint32_t*>(gen + OFF_BAR + 192);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NT = p.D / PE_N;
@@ -77,8 +104,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
 
   if (tid == 0) {
     auto init = [](uint32_t bar, unsigned cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt) : "memory"); };
-    for (int i = 0; i < 2; ++i) { init(s_full + 8 * i, 1); init(s_empty + 8 * i, 4); init(acc_full + 8 * i, 1); init(acc_empty + 8 * i, 4); }
-    for (int i = 0; i < 4; ++i) { init(a_full + 8 * i, 128); init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < PP_NSTAGE; ++i) { init(s_full + 8 * i, 1); init(s_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { init(acc_full + 8 * i, 1); init(acc_empty + 8 * i, 4); init(a_full + 8 * i, 4); init(a_empty + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -100,6 +127,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
   if (warp == 0) {
     // =============================== TMA producer ===============================
     unsigned q = 0;
+    PP_TDECL();
     for (int64_t tile = cta_in_col; tile < n_tiles; tile += ctas_per_col) {
       int row[2], x0[2];
       bool valid[2];
@@ -115,8 +143,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
       }
       const unsigned bytes = (valid[0] ? PP_SEG_BYTES : 0) + (valid[1] ? PP_SEG_BYTES : 0);
       for (int c = 0; c < PE_NKB; ++c, ++q) {
-        const unsigned stage = q & 1u, n = q >> 1;
-        if (n >= 1) pe_mbar_wait(s_empty + 8 * stage, (n - 1) & 1u);
+        const unsigned stage = q % PP_NSTAGE, n = q / PP_NSTAGE;
+        if (n >= 1) PP_TW(0, pe_mbar_wait(s_empty + 8 * stage, (n - 1) & 1u));
         if (lane == 0) {
           const uint32_t bar = s_full + 8 * stage;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -131,44 +159,50 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
         __syncwarp();
       }
     }
+    PP_TFLUSH(0, 0);
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(PE_N >> 3) << 17) | ((uint32_t)(PE_M >> 4) << 24);
-    unsigned k = 0;
+    unsigned k = 0, q = 0;
+    PP_TDECL();
     for (int64_t tile = cta_in_col; tile < n_tiles; tile += ctas_per_col, ++k) {
       const unsigned buf = k & 1u, m = k >> 1;
-      if (m >= 1) pe_mbar_wait(acc_empty + 8 * buf, (m - 1) & 1u);      // the epilogue has drained this accumulator
+      if (m >= 1) PP_TW(1, pe_mbar_wait(acc_empty + 8 * buf, (m - 1) & 1u));      // the epilogue has drained this accumulator
       const uint32_t acc_addr = tmem + buf * 256u;
-      for (int c = 0; c < PE_NKB; ++c) {
-        pe_mbar_wait(a_full + 8 * c, k & 1u);
+      for (int c = 0; c < PE_NKB; ++c, ++q) {
+        const unsigned slot = q & 1u;
+        PP_TW(0, pe_mbar_wait(a_full + 8 * slot, (q >> 1) & 1u));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t da = pe_desc(sA_a + c * PE_A_KB_BYTES + k4 * 32);
+            // A straight from TMEM (row = lane, 8 columns = 16 fp16 taps per K step), W from shared memory
+            const uint32_t ta = tmem + (slot ? PP_ACOL1 : PP_ACOL0) + 8u * k4;
             const uint64_t db = pe_desc(sB_a + c * PE_B_KB_BYTES + k4 * 32);
             const uint32_t acc = (c | k4) ? 1u : 0u;
             asm volatile(
                 "{\n"
                 ".reg .pred p;\n"
                 "setp.ne.b32 p, %4, 0;\n"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-                "}\n" ::"r"(acc_addr), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+                "}\n" ::"r"(acc_addr), "r"(ta), "l"(db), "r"(idesc), "r"(acc) : "memory");
           }
           // frees the A chunk once the MMAs that read it have completed; the last chunk also publishes the accumulator
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_empty + 8 * c) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_empty + 8 * slot) : "memory");
           if (c == PE_NKB - 1)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(acc_full + 8 * buf) : "memory");
         }
         __syncwarp();
       }
     }
+    PP_TFLUSH(0, 4); PP_TFLUSH(1, 5);
   } else if (warp >= 8) {
     // =============================== cutters: strips -> A chunks ===============================
     const int ct = tid - 256;                                           // A row = TMEM lane
     const int s = ct >> 6, slot = ct & (PP_SEG - 1);
     const bool even = (p.stride & 1) == 0;
     unsigned q = 0, k = 0;
+    PP_TDECL();
     for (int64_t tile = cta_in_col; tile < n_tiles; tile += ctas_per_col, ++k) {
       const int64_t G = 2 * tile + s;
       const bool valid = G < n_segs;
@@ -176,22 +210,26 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
       const int j = valid ? (int)(G - S * nseg) : 0;
       const bool live = valid && slot < segp && j * segp + slot < p.Tp;
       const int col0 = ((j * segp * p.stride) & 3) + slot * p.stride;   // first frame of the patch inside the staged strip
+      int off[8];                                                       // byte offset of the pair (col0 + 2 u, + 1) in row 0 of the segment
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int col = col0 + 2 * u;                                   // even stride: a pair never straddles the two boxes
+        off[u] = (col >> 8) * PP_BOX_BYTES + (col & 255) * 4;
+      }
       for (int c = 0; c < PE_NKB; ++c, ++q) {
-        const unsigned stage = q & 1u, n = q >> 1;
-        pe_mbar_wait(s_full + 8 * stage, n & 1u);
-        if (k >= 1) pe_mbar_wait(a_empty + 8 * c, (k - 1) & 1u);
+        const unsigned stage = q % PP_NSTAGE, n = q / PP_NSTAGE, slot = q & 1u, u_ = q >> 1;
+        PP_TW(0, pe_mbar_wait(s_full + 8 * stage, n & 1u));
+        if (u_ >= 1) PP_TW(1, pe_mbar_wait(a_empty + 8 * slot, (u_ - 1) & 1u));
+        [[maybe_unused]] const long long tcut_ = PP_NOW();
         const uint8_t* src = sS + stage * PP_STAGE_BYTES + s * PP_SEG_BYTES;
-        uint8_t* dstrow = sA + c * PE_A_KB_BYTES;
+        uint32_t r[32];                                                 // the row's 64 taps of this chunk as fp16 pairs: column 8 fl + u
 #pragma unroll
         for (int fl = 0; fl < 4; ++fl) {                                // feature row 4 c + fl of the patch: taps 16 fl .. 16 fl + 15
           float2 v[8];
           if (live) {
             if (even) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int col = col0 + 2 * u;                           // even: a pair never straddles the two boxes
-                v[u] = *reinterpret_cast<const float2*>(src + (col >> 8) * PP_BOX_BYTES + fl * (PP_BOXW * 4) + (col & 255) * 4);
-              }
+              for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float2*>(src + off[u] + fl * (PP_BOXW * 4));
             } else {
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
@@ -204,25 +242,34 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = make_float2(0.f, 0.f);
           }
-          uint4 lo, hi;
-          __half2 h;
-          h = __floats2half2_rn(v[0].x, v[0].y); lo.x = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[1].x, v[1].y); lo.y = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[2].x, v[2].y); lo.z = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[3].x, v[3].y); lo.w = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[4].x, v[4].y); hi.x = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[5].x, v[5].y); hi.y = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[6].x, v[6].y); hi.z = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[7].x, v[7].y); hi.w = *reinterpret_cast<uint32_t*>(&h);
-          *reinterpret_cast<uint4*>(dstrow + pe_swz(ct, 2 * fl)) = lo;
-          *reinterpret_cast<uint4*>(dstrow + pe_swz(ct, 2 * fl + 1)) = hi;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const __half2 h = __floats2half2_rn(v[u].x, v[u].y);
+            r[8 * fl + u] = *reinterpret_cast<const uint32_t*>(&h);
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
-        pp_arrive(a_full + 8 * c);
+        PP_TADD(3, tcut_);                                              // strip reads + conversion
+        [[maybe_unused]] const long long tst_ = PP_NOW();
+        // registers -> TMEM: lane = A row, 32 columns; no shared-memory round trip and no proxy fence for the A operand
+        const uint32_t ta = tmem + ((uint32_t)(32 * (warp - 8)) << 16) + (slot ? PP_ACOL1 : PP_ACOL0);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                     "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                     ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+                       "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                       "r"(r[30]), "r"(r[31]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) pp_arrive(s_empty + 8 * stage);                  // the warp has read its part of the strips
+        if (lane == 0) {                                                // one arrival per warp on either barrier
+          pp_arrive(a_full + 8 * slot);
+          pp_arrive(s_empty + 8 * stage);                               // the warp has read its part of the strips
+        }
+        PP_TADD(2, tcut_);
+        PP_TADD(4, tst_);                                               // tcgen05.st + wait + arrivals
       }
     }
+    PP_TFLUSH(0, 1); PP_TFLUSH(1, 2); PP_TFLUSH(2, 3); PP_TFLUSH(3, 9); PP_TFLUSH(4, 10);
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const int ew = warp - 4;                                            // TMEM lanes 32 ew .. 32 ew + 31
@@ -231,6 +278,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
     constexpr int NPASS = OUT_F16 ? 2 : 4, CPP = PE_N / NPASS, LD = CPP / 16;   // columns per pass, x16 loads per pass
     uint8_t* st = sStage + ew * (32 * PP_STG_ROW);
     unsigned k = 0;
+    PP_TDECL();
     for (int64_t tile = cta_in_col; tile < n_tiles; tile += ctas_per_col, ++k) {
       const unsigned buf = k & 1u, m = k >> 1;
       const int64_t G = 2 * tile + s;
@@ -241,11 +289,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
       int n_rows = segp - slot0 < p.Tp - tp0 ? segp - slot0 : p.Tp - tp0;
       n_rows = !valid ? 0 : (n_rows < 0 ? 0 : (n_rows > 32 ? 32 : n_rows));
       const int64_t m0 = S * p.Tp + tp0;                                // output row of lane 0 (rows are consecutive)
-      pe_mbar_wait(acc_full + 8 * buf, m & 1u);
+      PP_TW(0, pe_mbar_wait(acc_full + 8 * buf, m & 1u));
+      [[maybe_unused]] const long long tep_ = PP_NOW();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ps = 0; ps < NPASS; ++ps) {
         uint32_t v[LD][16];
+        [[maybe_unused]] const long long tld_ = PP_NOW();
 #pragma unroll
         for (int cc = 0; cc < LD; ++cc)
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -254,6 +304,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
                          "=r"(v[cc][13]), "=r"(v[cc][14]), "=r"(v[cc][15])
                        : "r"(tmem + ((uint32_t)(32 * ew) << 16) + buf * 256u + (uint32_t)(ps * CPP + 16 * cc)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        PP_TADD(3, tld_);
         if (ps == NPASS - 1) {                                          // the accumulator is in registers: hand it back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -281,8 +332,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
             h = __floats2half2_rn(f[10], f[11]); b2.y = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(f[12], f[13]); b2.z = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(f[14], f[15]); b2.w = *reinterpret_cast<uint32_t*>(&h);
-            reinterpret_cast<uint4*>(d)[0] = a;
-            reinterpret_cast<uint4*>(d)[1] = b2;
+            if (lane < n_rows)                                        // (slots past the segment's patches are not staged)
+            { reinterpret_cast<uint4*>(d)[0] = a; reinterpret_cast<uint4*>(d)[1] = b2; }
           } else {
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) reinterpret_cast<float4*>(d)[qd] = make_float4(f[4 * qd], f[4 * qd + 1], f[4 * qd + 2], f[4 * qd + 3]);
@@ -290,15 +341,37 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
         }
         __syncwarp();
         // n_rows rows x 12 chunks of 16 B (192 B per row and pass); consecutive lanes take consecutive chunks of a row
-        for (int idx = lane; idx < n_rows * 12; idx += 32) {
-          const int rr = idx / 12, ch = idx - rr * 12;
-          const uint4 val = *reinterpret_cast<const uint4*>(st + rr * PP_STG_ROW + 16 * ch);
-          uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + rr) * p.D + n0 + ps * CPP) * EB + 16 * ch;
-          __stcs(reinterpret_cast<uint4*>(o), val);
+        // (fully unrolled with a row predicate: the twelve staging reads are in flight together instead of one
+        // read -> store round trip per iteration)
+        uint8_t* const obase = reinterpret_cast<uint8_t*>(p.out) + ((size_t)m0 * p.D + n0 + ps * CPP) * EB;
+        const size_t opitch = (size_t)p.D * EB;
+        uint4 val[12];
+        [[maybe_unused]] const long long tsg_ = PP_NOW();
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+          const int idx = lane + 32 * it, rr = idx / 12, ch = idx - rr * 12;
+          val[it] = *reinterpret_cast<const uint4*>(st + rr * PP_STG_ROW + 16 * ch);
+        }
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+          const int idx = lane + 32 * it, rr = idx / 12, ch = idx - rr * 12;
+          if (rr < n_rows) __stcs(reinterpret_cast<uint4*>(obase + rr * opitch + 16 * ch), val[it]);
         }
         __syncwarp();
+        PP_TADD(4, tsg_);
       }
+      PP_TADD(1, tep_);
+#ifdef B200_PP_TIMING
+      tacc_[2] += 1ull;
+#endif
     }
+    PP_TFLUSH(0, 6); PP_TFLUSH(1, 7); PP_TFLUSH(3, 11);
+#ifdef B200_PP_TIMING
+    if (lane == 0) atomicAdd(&g_pp_timing[0] + 12, tacc_[4]);
+#endif
+#ifdef B200_PP_TIMING
+    if (ew == 0) PP_TFLUSH(2, 8);
+#endif
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
