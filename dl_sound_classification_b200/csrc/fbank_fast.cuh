@@ -412,6 +412,16 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       mbase = p.mix_bank + (size_t)j * p.out_frames * p.n_cols + (p.layout == 0 ? (size_t)t0 * p.n_cols : (size_t)t0);
     }
   }
+  // the partner's 4 x 4 cells of this lane are requested NOW, before the mel sums (the transform's registers are free
+  // again), so their latency -- L1 hits after the prefetch, L2 otherwise -- hides behind the mel phase
+  float mq[4][4];
+  if (MIX) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        mq[i][h] = (mbase != nullptr && i < fp.mel_groups && L.bin(i) >= 0 && t0 + h < row_end) ? __ldg(mbase + L.bin(i) + h * ostep) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= fp.mel_groups) continue;
@@ -454,12 +464,10 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
           const fk_u64 sc2 = fk_pk(L.scale(i), L.scale(i)), sh2 = fk_pk(L.shift(i), L.shift(i));
           float2 y01 = fk_upk(fk_fma2(fk_pk(v[0], v[1]), sc2, sh2)), y23 = fk_upk(fk_fma2(fk_pk(v[2], v[3]), sc2, sh2));
           if (MIX && mbase != nullptr) {                                                 // [phase: mixup_epilogue]
-            const float* q = mbase + moff;
-            const float q0 = __ldg(q), q1 = __ldg(q + ostep), q2 = __ldg(q + 2 * ostep), q3 = __ldg(q + 3 * ostep);
-            y01.x = __fadd_rn(__fmul_rn(mlam, y01.x), __fmul_rn(moml, q0));
-            y01.y = __fadd_rn(__fmul_rn(mlam, y01.y), __fmul_rn(moml, q1));
-            y23.x = __fadd_rn(__fmul_rn(mlam, y23.x), __fmul_rn(moml, q2));
-            y23.y = __fadd_rn(__fmul_rn(mlam, y23.y), __fmul_rn(moml, q3));
+            y01.x = __fadd_rn(__fmul_rn(mlam, y01.x), __fmul_rn(moml, mq[i][0]));
+            y01.y = __fadd_rn(__fmul_rn(mlam, y01.y), __fmul_rn(moml, mq[i][1]));
+            y23.x = __fadd_rn(__fmul_rn(mlam, y23.x), __fmul_rn(moml, mq[i][2]));
+            y23.y = __fadd_rn(__fmul_rn(mlam, y23.y), __fmul_rn(moml, mq[i][3]));
           }
           o[0] = y01.x; o[ostep] = y01.y; o[2 * ostep] = y23.x; o[3 * ostep] = y23.y;   // [phase: epilogue_store]
         } else {
@@ -470,7 +478,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
               // H9: pad rows are 0.0 before normalisation = the folded shift
               float y = (f0 + h) < nf ? fmaf(v[h], L.scale(i), L.shift(i)) : L.shift(i);
               if (t >= mk0 && t < mk0 + mk1) y = 0.f;
-              if (MIX && mbase != nullptr) y = __fadd_rn(__fmul_rn(mlam, y), __fmul_rn(moml, __ldg(mbase + moff + h * ostep)));
+              if (MIX && mbase != nullptr) y = __fadd_rn(__fmul_rn(mlam, y), __fmul_rn(moml, mq[i][h]));
               o[h * ostep] = y;
             }
           }
