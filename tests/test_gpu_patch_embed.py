@@ -67,13 +67,14 @@ def test_full_size_feeds_from_the_frontend(b2):
     assert tuple(spec.shape) == (1024, 1, 128, 512)
     torch.manual_seed(1)
     conv = torch.nn.Conv2d(1, 768, 16, stride=10).cuda()
-    y = b2.patch_embed(spec, conv.weight, conv.bias)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y = b2.patch_embed(spec, conv.weight, conv.bias)              # autocast: fp16 out, as the reference's 16-mixed trainer
     assert tuple(y.shape) == (1024, 600, 768) and y.dtype == torch.float16 and bool(torch.isfinite(y).all())
     idx = [0, 511, 1023]
     with torch.no_grad():
         ref = conv(spec[idx]).flatten(2).transpose(1, 2)
     assert float((y[idx].float() - ref).abs().max()) < 4e-3
-    assert torch.equal(b2.patch_embed(spec[idx], conv.weight, conv.bias), y[idx])          # batch invariance
+    assert torch.equal(b2.patch_embed(spec[idx], conv.weight.detach(), conv.bias.detach(), 10, torch.float16), y[idx])   # batch invariance
     with pytest.raises(NotImplementedError):
         b2.patch_embed(spec[:1], torch.zeros(100, 1, 16, 16), None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
@@ -106,3 +107,24 @@ def test_tma_pipeline_shapes_against_torch_convolution(b2, B, F, T, D, stride):
     assert float((half.float() - got).abs().max()) < 4e-3
     # repeated launches on one stream (barrier phases start from scratch every launch)
     assert torch.equal(b2.patch_embed(x, conv.weight, conv.bias, stride, torch.float32), got)
+
+
+def test_patch_embed_trains_through_the_kernel(b2):
+    """Swapping the module into a model that trains it must not freeze its parameters: the gradients of the kernel's
+    forward are the convolution's own (torch, on the GPU), and the default output type follows autocast."""
+    torch.manual_seed(5)
+    x = (torch.randn(2, 1, 128, 96) * 0.5).cuda().requires_grad_(True)
+    mod = b2.PatchEmbed(1, 192, 16, 10).cuda()
+    ref = torch.nn.Conv2d(1, 192, 16, stride=10).cuda()
+    ref.load_state_dict({"weight": mod.proj.weight.detach().clone(), "bias": mod.proj.bias.detach().clone()})
+    y = mod(x)
+    assert y.dtype == torch.float32 and y.requires_grad                   # no autocast: float32 like the reference module
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2 = x.detach().clone().requires_grad_(True)
+    ref(x2).flatten(2).transpose(1, 2).backward(g)
+    assert float((mod.proj.weight.grad - ref.weight.grad).abs().max()) < 2e-3 * float(ref.weight.grad.abs().max())
+    assert float((mod.proj.bias.grad - ref.bias.grad).abs().max()) < 1e-4 * float(ref.bias.grad.abs().max())
+    assert float((x.grad - x2.grad).abs().max()) < 1e-5 + 1e-4 * float(x2.grad.abs().max())
+    with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
+        assert mod(x).dtype == torch.float16

@@ -10,7 +10,7 @@ x = torch.randn((1024, 1, 128, 512), device="cuda") * 0.5
 conv = torch.nn.Conv2d(1, 768, 16, stride=10).cuda()
 buf = (ctypes.c_ulonglong * 16)()
 for it in range(3):
-    b2.patch_embed(x, conv.weight, conv.bias)
+    b2.patch_embed(x, conv.weight.detach(), conv.bias.detach(), 10, torch.float16)
     torch.cuda.synchronize()
     K.lib.b200fbank_debug_pp_timing(buf)
 v = list(buf)
