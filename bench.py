@@ -542,6 +542,18 @@ def run_extras(args, torch, dist, b2, dev, rank, world, barrier):
                                    "normalisation -> (256,1,128,1379)",
                           ms_per_step=ms, value=world * Bm * CLIP_SECONDS / (ms * 1e-3), unit=UNIT,
                           roofline_frac=alg / (ms * 1e-3) / 1e9 / peak)
+    del wm
+    # ---- AST patch embedding fed by the frontend's features ---------------
+    xs = torch.randn((1024, 1, N_MELS, OUT_FRAMES), generator=gen, device=dev)
+    w16 = (torch.randn((768, 1, 16, 16), generator=gen, device=dev) * 0.05)
+    pb = torch.zeros(768, device=dev)
+    ms = timed(lambda: b2.patch_embed(xs, w16, pb, 10, torch.float16), 20)
+    Mrows = 1024 * 12 * 50
+    alg = 1024 * N_MELS * OUT_FRAMES * 4 + Mrows * 768 * 2 + 768 * 256 * 2
+    out["patch_embed"] = dict(workload="1024 x (1,128,512) per GPU -> Conv2d(1,768,16,stride 10) + flatten -> (1024,600,768) fp16: TMA strips -> A in "
+                                       "tensor memory -> tcgen05.mma (patch_embed_pipe_kernel)",
+                              ms_per_step=ms, tflops=2.0 * Mrows * 768 * 256 / (ms * 1e-3) / 1e12,
+                              roofline_frac=alg / (ms * 1e-3) / 1e9 / peak)
     return out
 
 

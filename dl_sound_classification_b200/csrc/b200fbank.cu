@@ -826,7 +826,7 @@ int setup_fast(b200fbank_plan* p, std::vector<void*>& owned) {
     if (int rc = dev_copy(t48.data(), t48.size() * 4, (const void**)&f.ws_t48)) return rc;
     if (int rc = dev_copy(t22.data(), t22.size() * 4, (const void**)&f.ws_t22)) return rc;
     if (int rc = dev_copy(k22.data(), k22.size() * 4, (const void**)&f.ws_k22)) return rc;
-    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32) * 4 + 256;
+    p->ws_smem = (size_t)(WS_XFLOATS + WS_RING_FLOATS + WS_F_WARPS * FK_EBUF + 1024 + ((rows * 32 + 3) & ~3) + FK_LANE_ROWS * 32 + WS_F_WARPS * WS_PAD_COLS) * 4 + 256;
     // rates without the 44.1 kHz structure still run through this kernel's per-sample path
     p->ws_ok = (ok || f.fast_rate_id < 0) && !(kenv && strcmp(kenv, "fast") == 0) && p->ws_smem <= 227 * 1024;
     f.ws_ok = p->ws_ok;

@@ -162,6 +162,7 @@ __device__ __forceinline__ void ws_load_edge(const ClipInfo& c, int64_t in_lo, i
   fk_cp_async_wait_all();
 }
 
+constexpr int WS_PAD_COLS = 128;                              // columns of the per-warp pad-row table (the envelope's n_mel <= 128)
 constexpr int WS_QN = 8;                                      // depth of the item queue of the dynamic persistent form
 __device__ __forceinline__ int ws_claim(const FastParams& fp, int total) {
   const int id = (int)gridDim.x + atomicAdd(fp.ws_counter, 1);
@@ -216,7 +217,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
   float2* stw = reinterpret_cast<float2*>(ebuf + WS_F_WARPS * FK_EBUF);   // [512]
   float* smelw = reinterpret_cast<float*>(stw + 512);            // [mel_rows * 32]
   float* slane = smelw + ((fp.mel_rows * 32 + 3) & ~3);          // [FK_LANE_ROWS][32] static per-lane constants of the F warps
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slane + FK_LANE_ROWS * 32);   // full[3], empty[3], xfull
+  float* spad = slane + FK_LANE_ROWS * 32;                       // [8 F warps][WS_PAD_COLS] pad-row values of the current clip by column
+  uint64_t* bars = reinterpret_cast<uint64_t*>(spad + WS_F_WARPS * WS_PAD_COLS);   // full[3], empty[3], xfull
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = p.B * fp.segs;
@@ -595,6 +597,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
         const int m = __float_as_int(slane[(21 + i) * 32 + lane]);
         fk_fold_norm(p, STATS, AST || p.use_log, m, m >= mk2 && m < mk2 + mk3, L.nscale[i], L.nshift[i]);
       }
+      // Pure pad passes (four rows past the clip's last frame: 76 % of the rows of a US8K batch padded to 1024 frames) skip the
+      // frame pass: the pad value of a column is the folded shift (0.0 normalised), identical for every pad row of the clip,
+      // so such a pass is four 16-byte stores per lane.  (B, T, n_cols): values by column from a per-warp table;
+      // (B, 1, n_cols, T): the lane's own slot values, four frames of a bin are contiguous.
+      const bool pad_fast = !STATS && !MIX && (p.n_cols & 3) == 0 && p.n_cols <= WS_PAD_COLS && (p.out_frames & 3) == 0 &&
+                            (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+      float* padv = spad + wf * WS_PAD_COLS;
+      if (pad_fast && p.layout == 0) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < fp.mel_groups && L.mbin[i] >= 0) padv[L.mbin[i]] = L.nshift[i];
+        __syncwarp();
+      }
       const int row0 = (gch % WS_SLOTS) * 32;                    // ring row of the item's first hop
       for (int pp = (int)((wf - gpp) & (WS_F_WARPS - 1)); pp < it.pp_total; pp += WS_F_WARPS) {   // [phase: ws_frame_loop]
         bool waited = false;                                     // this slot has waited for (at least) its own chunk
@@ -615,6 +631,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           WS_TACC(4, tf0_);
 #endif
           const int row = (row0 + 4 * pp) % WS_RING_ROWS;
+          if (pad_fast && n_live == 0 && t0 + 4 <= it.row_end) {                       // [phase: ws_pad_rows]
+            if (p.layout == 0) {
+              const int c4 = 4 * lane;
+              if (c4 < p.n_cols) {
+                const float4 pv = *reinterpret_cast<const float4*>(padv + c4);
+                float* o = p.out + ((size_t)b * p.out_frames + t0) * p.n_cols + c4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int t = t0 + r;
+                  *reinterpret_cast<float4*>(o + (size_t)r * p.n_cols) = (t >= mk0 && t < mk0 + mk1) ? make_float4(0.f, 0.f, 0.f, 0.f) : pv;
+                }
+              }
+            } else {
+              float* o = p.out + (size_t)b * p.n_cols * p.out_frames + t0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < fp.mel_groups && L.mbin[i] >= 0) {
+                  const float sv = L.nshift[i];
+                  float4 v;
+                  v.x = (t0 >= mk0 && t0 < mk0 + mk1) ? 0.f : sv;         v.y = (t0 + 1 >= mk0 && t0 + 1 < mk0 + mk1) ? 0.f : sv;
+                  v.z = (t0 + 2 >= mk0 && t0 + 2 < mk0 + mk1) ? 0.f : sv; v.w = (t0 + 3 >= mk0 && t0 + 3 < mk0 + mk1) ? 0.f : sv;
+                  *reinterpret_cast<float4*>(o + L.mbin[i]) = v;
+                }
+            }
+          } else                                                                          // [phase: ws_frame_loop]
           fk_frame_pass<STATS, AST, FK_SHIFT, FkLane, MIX>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, it.row_end, lane,
                                               mk0, mk1, mk2, mk3, st_s, st_ss);
 #ifdef B200_WS_TIMING
