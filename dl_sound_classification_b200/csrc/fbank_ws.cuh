@@ -15,8 +15,8 @@
 //       3 -> 1 (48 kHz): one phase of 41 taps shared by all lanes, held as even- and odd-aligned pairs.
 //       441 -> 320 (22.05 kHz): 320 phases = two hops; even / odd R warps hold the taps of even / odd hops.
 //       anything else: per-sample loop (16 kHz input: plain copy).
-//     Interior input chunks (32 hops) arrive by ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx), the next
-//     chunk is pulled into L2 by a bulk prefetch meanwhile; chunks at a clip edge are assembled with cp.async + zero fill.
+//     Input chunks (32 hops) arrive by ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx), the next chunk is pulled
+//     into L2 by a bulk prefetch meanwhile; at a clip edge the lines outside / across the edge are assembled by hand.
 //   warpgroups 1-2 (8 "F" warps, 136 registers/thread after setmaxnreg.dec): frame passes of fbank_fast.cuh
 //     (DC/pre-emphasis/window, packed 512-point FFT, |.|^2, mel, log, epilogue, store), pass slot p -> warp p mod 8.
 //
@@ -361,7 +361,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
           x_parity ^= 1u;
         } else {
-          ws_load_edge(c, in_lo, nx, sh, xbuf, rt);
+          // Chunk at a clip edge (the first and the last of every clip): the 16-byte lines that lie inside the clip still
+          // come by ONE bulk copy; only the few lines that straddle the edge or lie outside it (zeros: the padding of
+          // torchaudio's conv, functional.py:1424) are assembled by hand.  (All by hand, this chunk cost the R warps as many
+          // instructions as resampling it.)
+          const int nvec = (nx + sh + 3) >> 2;
+          const int lo = in_lo < 0 ? (int)(-in_lo) : 0;            // first element index that exists in the clip
+          const int64_t hi64 = c.n_in - in_lo;                     // one past the last
+          const int hi = hi64 > nx + 8 ? nx + 8 : (hi64 < 0 ? 0 : (int)hi64);
+          int v_lo = (lo + sh + 3) >> 2, v_hi = (hi + sh) >> 2;    // vector slots [v_lo, v_hi) lie entirely inside the clip
+          v_hi = v_hi > nvec ? nvec : v_hi;
+          const bool bulk = v_hi >= v_lo + 64;
+          if (!bulk) v_lo = v_hi = 0;
+          if (bulk && rt == 0) ws_tma_load(xbuf + 4 * v_lo, gsrc - sh + 4 * v_lo, (unsigned)((v_hi - v_lo) << 4), bars + 2 * WS_SLOTS);
+          const int n_hand = v_lo + (nvec - v_hi);
+          for (int w = rt; w < n_hand; w += WS_R_THREADS) {
+            const int v = w < v_lo ? w : v_hi + (w - v_lo);
+            const int i0 = 4 * v - sh;
+            float4 x;
+            x.x = (i0 >= lo && i0 < hi) ? __ldg(gsrc + i0) : 0.f;
+            x.y = (i0 + 1 >= lo && i0 + 1 < hi) ? __ldg(gsrc + i0 + 1) : 0.f;
+            x.z = (i0 + 2 >= lo && i0 + 2 < hi) ? __ldg(gsrc + i0 + 2) : 0.f;
+            x.w = (i0 + 3 >= lo && i0 + 3 < hi) ? __ldg(gsrc + i0 + 3) : 0.f;
+            *reinterpret_cast<float4*>(xbuf + 4 * v) = x;
+          }
+          if (bulk) {
+            ws_mbar_wait(bars + 2 * WS_SLOTS, x_parity);
+            x_parity ^= 1u;
+          }
           ws_bar_r();
         }
         return sh;
