@@ -346,7 +346,7 @@ __device__ __forceinline__ void fk_frame_pass(const FbankParams& p, const FastPa
       }
     }
   }
-  if (f0 < nf) {
+  if (f0 < nf) {                                                                       // [phase: stage0_frames]
     const float dc_scale = p.remove_dc ? 1.f / (float)FK_SIZE : 0.f;
     // the two packed transforms (frames 0,1 and 2,3); unrolled so their dependency chains interleave (a rolled loop
     // halves the code but measured 3% slower: the pass is latency-bound, not instruction-cache bound)

@@ -3,8 +3,8 @@ usage (GPU box): python tools/ws_timing.py"""
 import ctypes, os, sys, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-lib_dir = os.path.join(ROOT, "dl_sound_classification_b200", "lib")
-shutil.copy(os.path.join(ROOT, "tools", "libb200fbank_timing.so"), os.path.join(lib_dir, "libb200fbank.so"))
+# run as: B200FBANK_LIB=$PWD/tools/build/ws_timing.so python tools/ws_timing.py   (nvcc ... -DB200_WS_TIMING -o tools/build/ws_timing.so)
+assert "B200FBANK_LIB" in os.environ, "point B200FBANK_LIB at a library built with -DB200_WS_TIMING"
 import torch
 import dl_sound_classification_b200 as b2
 from dl_sound_classification_b200 import _capi as K
