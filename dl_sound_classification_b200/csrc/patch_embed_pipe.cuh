@@ -29,7 +29,11 @@
 
 namespace b200 {
 
-constexpr int PP_THREADS = 384;
+#ifndef B200_PP_CUT_WARPS
+#define B200_PP_CUT_WARPS 4
+#endif
+constexpr int PP_CUT_WARPS = B200_PP_CUT_WARPS;         // 4: one cutter thread per A row and chunk; 8: two (feature rows 0-1 / 2-3 of the chunk)
+constexpr int PP_THREADS = 256 + 32 * PP_CUT_WARPS;
 constexpr int PP_SEG = 64;                               // row slots per segment (2 segments = the 128 rows of a tile)
 constexpr int PP_BOXW = 256;                             // floats per TMA box row (the box limit)
 constexpr int PP_BOX_BYTES = 4 * PP_BOXW * 4;            // 4 feature rows x 256 frames
@@ -104,8 +108,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
 
   if (tid == 0) {
     auto init = [](uint32_t bar, unsigned cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt) : "memory"); };
-    for (int i = 0; i < PP_NSTAGE; ++i) { init(s_full + 8 * i, 1); init(s_empty + 8 * i, 4); }
-    for (int i = 0; i < 2; ++i) { init(acc_full + 8 * i, 1); init(acc_empty + 8 * i, 4); init(a_full + 8 * i, 4); init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < PP_NSTAGE; ++i) { init(s_full + 8 * i, 1); init(s_empty + 8 * i, PP_CUT_WARPS); }
+    for (int i = 0; i < 2; ++i) { init(acc_full + 8 * i, 1); init(acc_empty + 8 * i, 4); init(a_full + 8 * i, PP_CUT_WARPS); init(a_empty + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -198,7 +202,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
     PP_TFLUSH(0, 4); PP_TFLUSH(1, 5);
   } else if (warp >= 8) {
     // =============================== cutters: strips -> A chunks ===============================
-    const int ct = tid - 256;                                           // A row = TMEM lane
+    const int ct = (tid - 256) & 127;                                   // A row = TMEM lane
+    constexpr int NFL = 16 / PP_CUT_WARPS;                              // feature rows of a chunk per cutter thread (4 or 2)
+    const int fl0 = ((tid - 256) >> 7) * NFL;
     const int s = ct >> 6, slot = ct & (PP_SEG - 1);
     const bool even = (p.stride & 1) == 0;
     unsigned q = 0, k = 0;
@@ -222,9 +228,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
         if (u_ >= 1) PP_TW(1, pe_mbar_wait(a_empty + 8 * slot, (u_ - 1) & 1u));
         [[maybe_unused]] const long long tcut_ = PP_NOW();
         const uint8_t* src = sS + stage * PP_STAGE_BYTES + s * PP_SEG_BYTES;
-        uint32_t r[32];                                                 // the row's 64 taps of this chunk as fp16 pairs: column 8 fl + u
+        uint32_t r[8 * NFL];                                            // the row's taps of this chunk as fp16 pairs: column 8 fl + u
 #pragma unroll
-        for (int fl = 0; fl < 4; ++fl) {                                // feature row 4 c + fl of the patch: taps 16 fl .. 16 fl + 15
+        for (int fi = 0; fi < NFL; ++fi) {                              // feature row 4 c + fl of the patch: taps 16 fl .. 16 fl + 15
+          const int fl = fl0 + fi;
           float2 v[8];
           if (live) {
             if (even) {
@@ -245,19 +252,26 @@ __global__ void __launch_bounds__(PP_THREADS, 1) patch_embed_pipe_kernel(const P
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const __half2 h = __floats2half2_rn(v[u].x, v[u].y);
-            r[8 * fl + u] = *reinterpret_cast<const uint32_t*>(&h);
+            r[8 * fi + u] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
         PP_TADD(3, tcut_);                                              // strip reads + conversion
         [[maybe_unused]] const long long tst_ = PP_NOW();
         // registers -> TMEM: lane = A row, 32 columns; no shared-memory round trip and no proxy fence for the A operand
-        const uint32_t ta = tmem + ((uint32_t)(32 * (warp - 8)) << 16) + (slot ? PP_ACOL1 : PP_ACOL0);
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-                     "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                     ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-                       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-                       "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-                       "r"(r[30]), "r"(r[31]) : "memory");
+        const uint32_t ta = tmem + ((uint32_t)(32 * (ct >> 5)) << 16) + (slot ? PP_ACOL1 : PP_ACOL0) + 8u * fl0;
+        if constexpr (NFL == 4) {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                       "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                       ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8 % (8 * NFL)]), "r"(r[9 % (8 * NFL)]),
+                         "r"(r[10 % (8 * NFL)]), "r"(r[11 % (8 * NFL)]), "r"(r[12 % (8 * NFL)]), "r"(r[13 % (8 * NFL)]), "r"(r[14 % (8 * NFL)]), "r"(r[15 % (8 * NFL)]),
+                         "r"(r[16 % (8 * NFL)]), "r"(r[17 % (8 * NFL)]), "r"(r[18 % (8 * NFL)]), "r"(r[19 % (8 * NFL)]), "r"(r[20 % (8 * NFL)]), "r"(r[21 % (8 * NFL)]),
+                         "r"(r[22 % (8 * NFL)]), "r"(r[23 % (8 * NFL)]), "r"(r[24 % (8 * NFL)]), "r"(r[25 % (8 * NFL)]), "r"(r[26 % (8 * NFL)]), "r"(r[27 % (8 * NFL)]),
+                         "r"(r[28 % (8 * NFL)]), "r"(r[29 % (8 * NFL)]), "r"(r[30 % (8 * NFL)]), "r"(r[31 % (8 * NFL)]) : "memory");
+        } else {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                       ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
