@@ -45,7 +45,10 @@ __device__ unsigned long long g_ws_timing[8];
 #endif
 
 constexpr int WS_THREADS = 384;
-constexpr unsigned WS_WAIT_HINT_NS = 2000;                    // try_wait suspend-time hint: a waiting warp sleeps instead of polling every ~40 cycles
+#ifndef B200_WS_HINT_NS
+#define B200_WS_HINT_NS 2000
+#endif
+constexpr unsigned WS_WAIT_HINT_NS = B200_WS_HINT_NS;                    // try_wait suspend-time hint: a waiting warp sleeps instead of polling every ~40 cycles
 constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;                // warpgroup 0 = R warps, warpgroups 1-2 = F warps (2 R + 10 F measured slower: 0.82 vs 0.75 ms)
 constexpr int WS_R_ITERS = 32 / WS_R_WARPS;                   // hops per R warp per chunk
 constexpr int WS_R_THREADS = 32 * WS_R_WARPS;
@@ -436,8 +439,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
 #ifdef B200_WS_TIMING
           const long long ta_ = clock64();
 #endif
-          if (nh2 > 0) prefetch_x((hop0 + 32) * FK_ORIG - FK_WIDTH, (nh2 - 1) * FK_ORIG + FK_KLEN + 8);
+          // (the prefetch of the NEXT chunk goes out after this chunk's copy has landed: issued before it, the copy queued
+          // behind the prefetch's DRAM fetch in the SM's bulk-copy engine and took 2.6 k cycles instead of an L2 hit's ~1 k)
           const int sh = stage_x(hop0 * FK_ORIG - FK_WIDTH, (nh - 1) * FK_ORIG + FK_KLEN + 8);
+          if (nh2 > 0) prefetch_x((hop0 + 32) * FK_ORIG - FK_WIDTH, (nh2 - 1) * FK_ORIG + FK_KLEN + 8);
 #ifdef B200_WS_TIMING
           const long long tb_ = clock64();
           WS_TACC(0, ta_);
@@ -481,8 +486,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           // ------------ 3 -> 1 (48 kHz): ONE phase of 41 taps shared by every lane; lane = outputs 5g..5g+4 of a hop, whose
           // windows start 3 samples apart: even starts pair the taps as (h[2i], h[2i+1]) = He, odd starts as (h[2i-1], h[2i])
           // = Ho.  Lanes read x at stride 15 (odd): conflict free without any rotation.       // [phase: ws_resample_48k]
-          if (nh2 > 0) prefetch_x((hop0 + 32) * (3 * FK_SHIFT) - WS_W48, (nh2 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
           const int sh = stage_x(hop0 * (3 * FK_SHIFT) - WS_W48, (nh * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
+          if (nh2 > 0) prefetch_x((hop0 + 32) * (3 * FK_SHIFT) - WS_W48, (nh2 * FK_SHIFT - 1) * 3 + 2 * WS_W48 + 3 + 8);
           if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
           const float* xs = xbuf + sh + 3 * FK_RP * g;
 #pragma unroll 1
@@ -511,8 +516,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           // its slack so that the 32 starts are distinct mod 32: conflict free without rotation.  // [phase: ws_resample_22k]
           const int par = rw & 1;
           const int np = (nh + 1) >> 1;                          // periods (pairs of hops) of this chunk; hop0 is even
-          if (nh2 > 0) prefetch_x(((hop0 >> 1) + 16) * FK_ORIG - WS_W22, (((nh2 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
           const int sh = stage_x((hop0 >> 1) * FK_ORIG - WS_W22, (np - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
+          if (nh2 > 0) prefetch_x(((hop0 >> 1) + 16) * FK_ORIG - WS_W22, (((nh2 + 1) >> 1) - 1) * FK_ORIG + FK_ORIG + 2 * WS_W22 + 8);
           if (gc >= WS_SLOTS) ws_mbar_wait(bars + WS_SLOTS + slot, (unsigned)((gc / WS_SLOTS - 1) & 1));
           const float* xs = xbuf + sh + k0;
 #pragma unroll 1
