@@ -460,6 +460,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
           const int skew = (9 * ((g & 15) - (((sh + k0 + FK_ORIG * pg) >> 1) & 15))) & 15;
           const float* xs = xbuf + sh + k0 + pg * FK_ORIG;
           const int s0 = WS_R_ITERS * (rw & 1) + skew;
+#ifdef B200_WS_SKIP_R                                                                     // timing experiment only: no resampling
+          if (false)
+#endif
           if (cls == 0) {
 #pragma unroll 1
             for (int i = 0; i < WS_R_ITERS; ++i) {
@@ -688,6 +691,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fbank_ws_kernel(const FbankPara
                 }
             }
           } else                                                                          // [phase: ws_frame_loop]
+#ifdef B200_WS_SKIP_F                                                                     // timing experiment only: the F warps do nothing
+          if (false)
+#endif
           fk_frame_pass<STATS, AST, FK_SHIFT, FkLane, MIX>(p, fp, L, ring + row * FK_SHIFT, Ebuf, stw, smelw, b, t0, n_live, it.row_end, lane,
                                               mk0, mk1, mk2, mk3, st_s, st_ss);
 #ifdef B200_WS_TIMING
