@@ -52,7 +52,11 @@ constexpr unsigned WS_WAIT_HINT_NS = B200_WS_HINT_NS;                    // try_
 constexpr int WS_R_WARPS = 4, WS_F_WARPS = 8;                // warpgroup 0 = R warps, warpgroups 1-2 = F warps (2 R + 10 F measured slower: 0.82 vs 0.75 ms)
 constexpr int WS_R_ITERS = 32 / WS_R_WARPS;                   // hops per R warp per chunk
 constexpr int WS_R_THREADS = 32 * WS_R_WARPS;
-constexpr int WS_SLOTS = 3;
+#ifndef B200_WS_SLOTS
+#define B200_WS_SLOTS 3
+#endif
+static_assert(B200_WS_SLOTS >= 2 && B200_WS_SLOTS <= 3, "bars[8]: full[], empty[], the TMA barrier; a fourth slot needs a ninth");
+constexpr int WS_SLOTS = B200_WS_SLOTS;                      // ring slots of 32 hops (2 measured 16 % slower: the R warps must be able to run two chunks ahead)
 constexpr int WS_RING_ROWS = 32 * WS_SLOTS;                   // 96 hops
 constexpr int WS_MIRROR = 6;                                  // rows 96..101 repeat rows 0..5
 constexpr int WS_RING_FLOATS = (WS_RING_ROWS + WS_MIRROR) * FK_SHIFT;   // 16320
