@@ -159,3 +159,39 @@ def test_stats_pass(b2, O, golden):
     keep = np.arange(128) != 3                                             # filter #3 is constant: std == 0
     np.testing.assert_allclose(std_b[keep], rs[keep], rtol=1e-4)
     assert abs(gm - rgm) <= 1e-4 * abs(rgm) and abs(gs - rgs) <= 1e-4 * rgs
+
+
+@pytest.mark.parametrize("seed,table", [(1, (44100,)), (2, (44100,)), (3, (22050, 44100, 48000)), (4, (16000, 44100))])
+def test_tuned_kernel_agrees_with_the_generic_kernel_on_random_ragged_batches(b2, seed, table, monkeypatch):
+    """Fuzz of the persistent kernel's edge handling (clip-edge chunks by bulk copy + hand-assembled lines, pad-row fast
+    path, crops, masks reaching into pad rows, clips shorter than a window) against the correctness-first generic kernel
+    of the same plan options: same frame counts, same zero pattern, log-mel within the bar."""
+    g = torch.Generator().manual_seed(100 + seed)
+    B = 96
+    rid = torch.randint(0, len(table), (B,), generator=g)
+    rates = torch.tensor(table)[rid]
+    dur = torch.exp(torch.rand(B, generator=g) * 5.0 - 4.6)                      # 0.01 .. 1.5 s, log-uniform
+    lens = (dur * rates).long().clamp(min=1)
+    lens[0] = 399 * int(rates[0]) // 16000                                       # shorter than one analysis window
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    flat = (torch.rand(int(offsets[-1]), generator=g) * 2 - 1).cuda()
+    fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    monkeypatch.setenv("B200FBANK_KERNEL", "generic")
+    ref_fe = b2.FbankFrontend(orig_rates=table, **b2.AST_FBANK_KWARGS)
+    monkeypatch.delenv("B200FBANK_KERNEL")
+    for T, layout in ((64, "btf"), (100, "bft"), (130, "btf"), (152, "bft")):
+        masks = torch.stack([torch.randint(0, T, (B,), generator=g), torch.randint(0, T // 3, (B,), generator=g),
+                             torch.randint(0, 100, (B,), generator=g), torch.randint(0, 28, (B,), generator=g)], 1).int()
+        masks[:, 1] = torch.minimum(masks[:, 1], T - masks[:, 0])
+        kw = dict(offsets=offsets, rate_ids=rid.int(), masks=masks, mean=-4.27, std=4.57, layout=layout)
+        got, n1 = fe(flat, T, **kw)
+        want, n2 = ref_fe(flat, T, **kw)
+        assert torch.equal(n1, n2) and int(n1[0]) == 0
+        a, b_ = got.cpu().numpy(), want.cpu().numpy()
+        assert ((a == 0) == (b_ == 0)).all(), (T, layout)
+        if layout == "bft":
+            a, b_ = a[:, 0].transpose(0, 2, 1), b_[:, 0].transpose(0, 2, 1)
+        # back to log-mel units for the parity bar: y = (x - mean) / (2 std); pad rows and masked cells (0.0 in both) drop out
+        live = a != 0
+        assert_logmel_close(np.where(live, a * (2 * 4.57) - 4.27, 0.0), np.where(live, b_ * (2 * 4.57) - 4.27, 0.0), LOGMEL_TOL,
+                            f"fuzz seed {seed} T {T} {layout}", 1e-3)
