@@ -128,3 +128,26 @@ def test_patch_embed_trains_through_the_kernel(b2):
     assert float((x.grad - x2.grad).abs().max()) < 1e-5 + 1e-4 * float(x2.grad.abs().max())
     with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
         assert mod(x).dtype == torch.float16
+
+
+def test_tma_pipeline_random_shapes(b2):
+    """Fuzz of the segmentation logic (segments per patch row, patches per segment, tail tiles, strip alignment) of the
+    pipelined kernel: random feature-map shapes and strides against torch's convolution of the fp16-rounded operands."""
+    g = torch.Generator().manual_seed(2025)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for _ in range(12):
+            B = int(torch.randint(1, 6, (1,), generator=g))
+            F = int(torch.randint(16, 140, (1,), generator=g))
+            T = 4 * int(torch.randint(4, 420, (1,), generator=g))
+            stride = int(torch.randint(4, 17, (1,), generator=g))
+            x = (torch.randn(B, 1, F, T, generator=g) * 0.5).cuda()
+            w = (torch.randn(192, 1, 16, 16, generator=g) * 0.05).cuda()
+            bias = torch.randn(192, generator=g).cuda()
+            ref = torch.nn.functional.conv2d(x.half().float(), w.half().float(), bias, stride=stride).flatten(2).transpose(1, 2)
+            got = b2.patch_embed(x, w, bias, stride, torch.float32)
+            assert tuple(got.shape) == tuple(ref.shape), (B, F, T, stride)
+            assert float((got - ref).abs().max()) < ATOL_VS_FP16_OPERANDS, (B, F, T, stride)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
